@@ -1,0 +1,79 @@
+/*
+ * sgm_oracle.h -- CPU restatement ("port") of the reference SGM hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or
+ * call it, and there only as the checker / the reported CPU baseline.
+ *
+ * Reference = /root/reference/SemiGlobalMatching/SemiGlobalMatching/SemiGlobalMatching.c
+ * (abbreviated SGM.c below).  Parity status: PINNED -- tests/test_oracle_vs_ref.py checks every
+ * stage of this restatement against the reference source itself, compiled verbatim by
+ * oracle/build_ref.py into oracle/_ref/ (guard rows + padded inputs), and against the
+ * committed fixtures in tests/golden/ that were generated from that build.
+ *
+ * Unlike the reference this code takes all sizes at run time, keeps no global state, and elides the
+ * out-of-bounds pixel visit the reference makes on two diagonal paths (SGM.c:297-310,325,345; the
+ * visit is the last one on its path, so eliding it cannot change any in-bounds value).
+ */
+#ifndef SGM_ORACLE_H
+#define SGM_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int32_t width, height;
+    int32_t min_disparity, max_disparity;   /* D = max - min                       SGM.c:49        */
+    int32_t num_paths;                      /* 4 = SGM.c:213-216 only, else all 8  SGM.c:213-220   */
+    int32_t p1, p2_init;                    /*                                     SGM.c:333-335   */
+    int32_t check_unique;  float uniqueness_ratio;      /*                         SGM.c:412-426   */
+    int32_t check_lr;      float lrcheck_thres;         /*                         SGM.c:102-111   */
+    int32_t remove_speckles; int32_t min_speckle_area;  /*                         SGM.c:113-117   */
+    int32_t median;                         /* reference: always 1                 SGM.c:120       */
+} sgmo_params;
+
+/* Optional stage taps; any pointer may be NULL.  Sizes: N = W*H, V = N*D. */
+typedef struct {
+    uint32_t *census_left, *census_right;   /* [N]                                                  */
+    uint8_t  *cost;                         /* [V]   C(p,d)                                         */
+    uint16_t *path_cost[8];                 /* [V]   contribution of direction r to S: L_r(p,d)     */
+                                            /*       summed over that direction's visits of p (a    */
+                                            /*       pixel can be visited 0, 1 or 2 times)          */
+    uint16_t *aggr;                         /* [V]   S(p,d)                                         */
+    float    *disp_left_wta;                /* [N]   left disparity before LR check                 */
+    float    *disp_right;                   /* [N]   right-view disparity (only when check_lr)      */
+    float    *disp_lr;                      /* [N]   after LR check (== north-star hot-path output) */
+    float    *disp_speckle;                 /* [N]   after speckle removal                          */
+} sgmo_taps;
+
+/* Stage functions (each cites the reference lines it restates in sgm_oracle.c). */
+void sgmo_census5x5(const uint8_t* img, int W, int H, uint32_t* census /* zero-filled by caller */);
+void sgmo_cost(const uint32_t* cl, const uint32_t* cr, int W, int H, int dmin, int dmax, uint8_t* C);
+/* Walk all paths of one direction; adds L_r into S (uint16) and, if contrib != NULL, also into contrib. */
+void sgmo_aggregate_dir(const uint8_t* img, const uint8_t* C, int W, int H, int D, int p1, int p2_init,
+                        int dx, int dy, uint16_t* S, uint16_t* contrib);
+void sgmo_wta(const uint16_t* S, int W, int H, int dmin, int dmax, int check_unique,
+              float uniqueness_ratio, int inverse, float* disp);
+void sgmo_lrcheck(float* disp_left, const float* disp_right, int W, int H, float thres);
+void sgmo_remove_speckles(float* disp, int W, int H, float diff_insame, int min_area);
+void sgmo_median3_inplace(float* disp, int W, int H);
+
+/* Pixel-index walker of one aggregation path (SGM.c:232-367).  Writes the path's pixel indices to
+ * pos[] (negative or >= W*H == the reference's out-of-bounds visit) and returns their count. */
+int sgmo_walk_path(int W, int H, int dx, int dy, int path, int64_t* pos);
+
+/* Whole pipeline == SGM_Initialize + SGM_Match (SGM.c:37-125).  Returns 0 on success, -1 on the
+ * argument errors the reference rejects (SGM.c:43-48,70-75). */
+int sgmo_match(const sgmo_params* prm, const uint8_t* left, const uint8_t* right, float* disp_out,
+               const sgmo_taps* taps);
+
+/* Hot path only (census .. LR check), for CPU-baseline timing. */
+int sgmo_match_hotpath(const sgmo_params* prm, const uint8_t* left, const uint8_t* right, float* disp_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
