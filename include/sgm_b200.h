@@ -1,0 +1,128 @@
+/*
+ * sgm_b200.h -- additive C-ABI of libsgm_b200.so (plain pointers and sizes only).
+ *
+ * The three reference entry points live in SemiGlobalMatching.h and keep the reference's signatures.
+ * Everything here is NEW surface that the reference does not have (last row):
+ * explicit contexts (the reference has one global instance, SemiGlobalMatching.c:27), device
+ * selection, stage taps (the reference exposes its global buffers instead, SemiGlobalMatching.h:67-72),
+ * device-pointer and batched entry points.  SGM_Initialize/SGM_Reset/SGM_Match are thin wrappers over
+ * a process-global context driven through these functions.
+ *
+ * All functions return 0 on success and a negative SGMB_E_* code on failure; none aborts, throws or
+ * falls back to a CPU implementation.  SGMB_LastError() gives a human-readable reason (thread-local).
+ */
+#ifndef SGM_B200_H
+#define SGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "SemiGlobalMatching.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SGMB_Context SGMB_Context;
+
+enum {
+    SGMB_OK = 0,
+    SGMB_E_ARG = -1,        /* the argument errors the reference rejects (SemiGlobalMatching.c:43-48,70-75) */
+    SGMB_E_UNSUPPORTED = -2,/* disparity range > 256, negative P1/P2, more than 65535 rows/columns        */
+    SGMB_E_CUDA = -3,       /* no device, allocation failure, launch failure                               */
+    SGMB_E_STATE = -4       /* not configured / stage not retained / wrong buffer size                     */
+};
+
+/* Pipeline switches (SGMB_SetPipeline).  Default = SGMB_PIPE_REFERENCE: what SGM_Match does. */
+enum {
+    SGMB_PIPE_SPECKLE = 1u << 0,  /* run the speckle filter when SGMOption.is_remove_speckles (SemiGlobalMatching.c:113-117) */
+    SGMB_PIPE_MEDIAN  = 1u << 1,  /* run the in-place 3x3 median (SemiGlobalMatching.c:120)                                  */
+    SGMB_PIPE_TAPS    = 1u << 2,  /* retain every intermediate stage for SGMB_GetStage (allocates the uint16 S volume)       */
+    SGMB_PIPE_REFERENCE = SGMB_PIPE_SPECKLE | SGMB_PIPE_MEDIAN,
+    SGMB_PIPE_HOTPATH = 0u        /* census .. LR check only: the north-star hot path                                         */
+};
+
+/* Stages readable with SGMB_GetStage after a Match (element type, element count; N = W*H, D = range). */
+enum {
+    SGMB_STAGE_CENSUS_LEFT   = 0,  /* uint32 [N]     census_transform_5x5       SemiGlobalMatching.c:134-159 */
+    SGMB_STAGE_CENSUS_RIGHT  = 1,  /* uint32 [N]                                                             */
+    SGMB_STAGE_AGGR          = 2,  /* uint16 [N*D]   S(p,d), reference layout   SemiGlobalMatching.c:198-372 (needs SGMB_PIPE_TAPS) */
+    SGMB_STAGE_DISP_LEFT_WTA = 3,  /* float  [N]     left view before LR check  SemiGlobalMatching.c:374-443 (needs SGMB_PIPE_TAPS) */
+    SGMB_STAGE_DISP_RIGHT    = 4,  /* float  [N]     right view                 SemiGlobalMatching.c:105     (needs SGMB_PIPE_TAPS) */
+    SGMB_STAGE_DISP_LR       = 5,  /* float  [N]     after LR check             SemiGlobalMatching.c:445-470 */
+    SGMB_STAGE_DISP_SPECKLE  = 6,  /* float  [N]     after speckle removal      SemiGlobalMatching.c:585-642 (needs SGMB_PIPE_TAPS) */
+    SGMB_STAGE_DISP_FINAL    = 7,  /* float  [N]     what SGM_Match returns                                   */
+    SGMB_STAGE_PATH_PLANE_0  = 16  /* uint8  [N*D]   +r: L_r(p,d) of direction r (order of SemiGlobalMatching.c:213-220) as written by
+                                      its regular paths; pixels on an irregular path hold 0 (needs SGMB_PIPE_TAPS) */
+};
+
+const char* SGMB_LastError(void);
+
+/* Number of CUDA devices visible, or a negative error. */
+int SGMB_DeviceCount(void);
+
+/* Create / destroy a context bound to one CUDA device.  `slots` (>= 1) is the number of frames that may
+ * be in flight at once in SGMB_MatchBatch*; each slot owns a stream and a full set of device buffers. */
+int  SGMB_Create(SGMB_Context** out, int device, int slots);
+void SGMB_Destroy(SGMB_Context* ctx);
+
+/* == SGM_Initialize on an explicit context. */
+int SGMB_Configure(SGMB_Context* ctx, uint16_t width, uint16_t height, const SGMOption* option);
+int SGMB_SetPipeline(SGMB_Context* ctx, unsigned flags);
+
+/* == SGM_Match: host pointers, blocking; H2D + kernels + D2H. */
+int SGMB_Match(SGMB_Context* ctx, const uint8_t* img_left, const uint8_t* img_right, float* disp_left);
+
+/* Device-resident variant: all three pointers are device memory on the context's device.  The work is
+ * enqueued on slot 0's stream; with `sync` != 0 the call returns after completion. */
+int SGMB_MatchDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int sync);
+int SGMB_Synchronize(SGMB_Context* ctx);
+
+/* Batch of n independent pairs, host pointers (pinned memory recommended: SGMB_HostAlloc), frames
+ * pipelined over the context's slots: copy-in, kernels and copy-out of different frames overlap. */
+int SGMB_MatchBatch(SGMB_Context* ctx, const uint8_t* const* lefts, const uint8_t* const* rights,
+                    float* const* disps, int n);
+/* Same with device-resident inputs and outputs (no PCIe traffic). */
+int SGMB_MatchBatchDevice(SGMB_Context* ctx, const uint8_t* const* d_lefts, const uint8_t* const* d_rights,
+                          float* const* d_disps, int n);
+
+/* Batch sharded over several GPUs of one box: pair k goes to device devices[k * ndev / n] (contiguous
+ * shards), one host worker thread and one private context per device, no inter-GPU communication. */
+int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots_per_device, uint16_t width, uint16_t height,
+                            const SGMOption* option, unsigned pipeline_flags, const uint8_t* const* lefts,
+                            const uint8_t* const* rights, float* const* disps, int n);
+
+/* Copy a retained stage of slot 0 to host memory; `bytes` must equal the stage's size. */
+int SGMB_GetStage(SGMB_Context* ctx, int stage, void* host_dst, size_t bytes);
+
+/* Pinned host memory helpers. */
+int  SGMB_HostAlloc(void** out, size_t bytes);
+void SGMB_HostFree(void* p);
+
+/* Introspection for benchmarks: kernels launched per frame by the current plan, algorithmic and
+ * actually-moved DRAM byte models, device-side time of the last SGMB_Match* in milliseconds. */
+int    SGMB_KernelLaunchesPerFrame(SGMB_Context* ctx);
+double SGMB_ModelBytesPerFrame(SGMB_Context* ctx);   /* W*H*(4*P*D + 6)                    */
+double SGMB_PlanBytesPerFrame(SGMB_Context* ctx);    /* bytes this implementation's plan moves (planes) */
+float  SGMB_LastDeviceMs(SGMB_Context* ctx);
+/* Time `iters` back-to-back device-resident frames on slot 0 with CUDA events on its stream, after
+ * `warmup` untimed ones; writes per-iteration milliseconds of the whole frame and of the dominant
+ * (aggregation) kernel.  flush_l2 != 0 overwrites a >L2-sized scratch buffer between iterations. */
+int SGMB_TimeDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int warmup,
+                    int iters, int flush_l2, float* frame_ms, float* aggr_kernel_ms);
+
+/* The context behind SGM_Initialize/SGM_Match (NULL before the first SGM_Initialize), and the device it
+ * will use (default 0, or env SGM_B200_DEVICE). */
+SGMB_Context* SGMB_GlobalContext(void);
+int SGMB_SetGlobalDevice(int device);
+
+/* Host-only views of the aggregation path topology (no CUDA call; usable without a GPU): the pixel indices
+ * one path visits (index outside [0, W*H) == the reference's out-of-bounds visit, which is skipped), and
+ * which paths of a direction (0..7, order of SemiGlobalMatching.c:213-220) leave their toroidal diagonal.
+ * Both return the number of entries written or a negative error. */
+int SGMB_DebugWalkPath(int width, int height, int direction, int path, int* positions, int capacity);
+int SGMB_DebugClassifyPaths(int width, int height, int direction, uint8_t* irregular, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGM_B200_H */

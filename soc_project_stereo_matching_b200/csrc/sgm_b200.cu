@@ -1,0 +1,676 @@
+// sgm_b200.cu -- host side and C-ABI of libsgm_b200.so (see include/SemiGlobalMatching.h, include/sgm_b200.h).
+//
+// Pipeline per frame (all on one stream, no host round trip in between):
+//   memset side buffer -> K1 census (both images) -> K2 aggregation (all paths of all directions, one
+//   launch) -> K3 plane sum + WTA(left,right) + sub-pixel + LR check -> [K4 speckle CCL] -> [K5 in-place
+//   median wavefront].
+// There is no CPU implementation behind these entry points: without a CUDA device they fail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sgm_b200.h"
+#include "aggregate.cuh"
+#include "census.cuh"
+#include "path_walker.h"
+#include "postproc.cuh"
+#include "wta.cuh"
+
+using namespace sgmb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SGMB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* SGMB_LastError(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ context
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evAgg0 = nullptr, evAgg1 = nullptr, evDone = nullptr;
+    uint8_t* img[2] = {nullptr, nullptr};
+    uint32_t* censusL = nullptr;
+    uint32_t* censusR4 = nullptr;
+    uint8_t* planes = nullptr;
+    uint16_t* side = nullptr;
+    uint16_t* S = nullptr;            // taps only
+    float* dispLeftWta = nullptr;     // taps only
+    float* dispRight = nullptr;       // taps only
+    float* dispLR = nullptr;
+    float* dispSpeckle = nullptr;
+    float* dispFinal = nullptr;
+    int32_t* labels = nullptr;        // speckle filter scratch [2N]
+    unsigned long long* xchg = nullptr;   // median wavefront exchange rows [(H+31)/32][W]
+    unsigned medianEpoch = 0;
+    bool busy = false;
+};
+
+struct SGMB_Context {
+    int device = 0;
+    int nslots = 1;
+    std::vector<Slot> slots;
+    bool configured = false;
+    unsigned pipeline = SGMB_PIPE_REFERENCE;
+    SGMOption opt{};
+    int W = 0, H = 0, D = 0, Dp = 0, NR = 0, nDirs = 8;
+    size_t N = 0;
+    int padF = 0;
+    size_t copyStride = 0, planeStride = 0;
+    // configuration-wide read-only device tables
+    PathWork* work = nullptr;
+    int nWork = 0;
+    int32_t* entryOf = nullptr;
+    int nEntries = 0, nIrregular = 0;
+    uint16_t* p2tab = nullptr;
+    int p1c = 0;
+    // K3 launch shape
+    int wtaTW = 128;
+    size_t wtaSmem = 0;
+    // L2 flush scratch for SGMB_TimeDevice
+    uint8_t* flushBuf = nullptr;
+    size_t flushBytes = 0;
+    float lastMs = 0.f;
+    bool tapsAllocated = false;
+};
+
+static int ensure_device(SGMB_Context* c)
+{
+    CU(cudaSetDevice(c->device));
+    return SGMB_OK;
+}
+
+static void free_slot_buffers(Slot& s)
+{
+    cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
+    cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
+    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg);
+    s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
+    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr;
+}
+
+static void free_config(SGMB_Context* c)
+{
+    for (auto& s : c->slots) free_slot_buffers(s);
+    cudaFree(c->work); cudaFree(c->entryOf); cudaFree(c->p2tab);
+    c->work = nullptr; c->entryOf = nullptr; c->p2tab = nullptr;
+    c->configured = false; c->tapsAllocated = false;
+}
+
+extern "C" int SGMB_DeviceCount(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(SGMB_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+extern "C" int SGMB_Create(SGMB_Context** out, int device, int slots)
+{
+    if (!out || slots < 1 || slots > 64) return fail(SGMB_E_ARG, "SGMB_Create: bad arguments");
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(SGMB_E_CUDA, "SGMB_Create: device %d not present (%d visible)", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SGMB_E_CUDA, "SGMB_Create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    auto* c = new SGMB_Context();
+    c->device = device;
+    c->nslots = slots;
+    c->slots.resize(slots);
+    CU(cudaSetDevice(device));
+    for (auto& s : c->slots) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s.evStart)); CU(cudaEventCreate(&s.evStop));
+        CU(cudaEventCreate(&s.evAgg0)); CU(cudaEventCreate(&s.evAgg1));
+        CU(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
+    }
+    *out = c;
+    return SGMB_OK;
+}
+
+extern "C" void SGMB_Destroy(SGMB_Context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_config(c);
+    cudaFree(c->flushBuf);
+    for (auto& s : c->slots) {
+        if (s.evStart) cudaEventDestroy(s.evStart);
+        if (s.evStop) cudaEventDestroy(s.evStop);
+        if (s.evAgg0) cudaEventDestroy(s.evAgg0);
+        if (s.evAgg1) cudaEventDestroy(s.evAgg1);
+        if (s.evDone) cudaEventDestroy(s.evDone);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------ path topology (host)
+// A path is regular iff its walk equals the toroidal diagonal at every visit (path_walker.h).
+static bool path_is_regular(int W, int H, int d, int path)
+{
+    if (d < 4) return true;
+    const Dir dir = direction(d);
+    PathWalker wk;
+    wk.start(W, H, dir.dx, dir.dy, path);
+    for (int s = 0; s < H; ++s) {
+        if (s) wk.advance();
+        if (wk.pos != regular_position(W, H, dir.dx, dir.dy, path, s)) return false;
+    }
+    return true;
+}
+
+extern "C" int SGMB_DebugWalkPath(int W, int H, int d, int path, int* out, int capacity)
+{
+    if (W <= 0 || H <= 0 || d < 0 || d > 7 || !out) return fail(SGMB_E_ARG, "SGMB_DebugWalkPath: bad arguments");
+    const Dir dir = direction(d);
+    PathWalker wk;
+    wk.start(W, H, dir.dx, dir.dy, path);
+    const int len = wk.length();
+    if (path < 0 || path >= (d < 2 ? H : W) || capacity < len) return fail(SGMB_E_ARG, "SGMB_DebugWalkPath: bad path/capacity");
+    for (int s = 0; s < len; ++s) {
+        if (s) wk.advance();
+        out[s] = wk.pos;
+    }
+    return len;
+}
+
+extern "C" int SGMB_DebugClassifyPaths(int W, int H, int d, uint8_t* irregular, int capacity)
+{
+    if (W <= 0 || H <= 0 || d < 0 || d > 7 || !irregular) return fail(SGMB_E_ARG, "SGMB_DebugClassifyPaths: bad arguments");
+    const int n = d < 2 ? H : W;
+    if (capacity < n) return fail(SGMB_E_ARG, "SGMB_DebugClassifyPaths: capacity");
+    for (int i = 0; i < n; ++i) irregular[i] = path_is_regular(W, H, d, i) ? 0 : 1;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ configure
+static int alloc_taps(SGMB_Context* c)
+{
+    if (c->tapsAllocated) return SGMB_OK;
+    for (auto& s : c->slots) {
+        CU(cudaMalloc(&s.S, c->N * (size_t)c->D * sizeof(uint16_t)));
+        CU(cudaMalloc(&s.dispLeftWta, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.dispRight, c->N * sizeof(float)));
+    }
+    c->tapsAllocated = true;
+    return SGMB_OK;
+}
+
+static size_t wta_smem_bytes(int TW, int D, int Dp, int W)
+{
+    const size_t ring = (size_t)(TW + D) * (Dp + 2) * 2;
+    return ((ring + 15) & ~(size_t)15) + 2 * (size_t)W * sizeof(float);
+}
+
+extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, const SGMOption* option)
+{
+    if (!c) return fail(SGMB_E_ARG, "SGMB_Configure: NULL context");
+    if (!option) return fail(SGMB_E_ARG, "SGMB_Configure: NULL option");
+    if (int rc = ensure_device(c)) return rc;
+    CU(cudaDeviceSynchronize());
+    free_config(c);
+    // the reference's own argument checks (SemiGlobalMatching.c:43-48)
+    if (width == 0 || height == 0) return fail(SGMB_E_ARG, "width/height must be non-zero");
+    if (option->max_disparity <= option->min_disparity) return fail(SGMB_E_ARG, "max_disparity must exceed min_disparity");
+    const int D = option->max_disparity - option->min_disparity;
+    if (D > 256) return fail(SGMB_E_UNSUPPORTED, "disparity range %d > 256 is not supported", D);
+    if (option->p1 < 0 || option->p2_init < 0) return fail(SGMB_E_UNSUPPORTED, "negative P1/P2 are not supported");
+    if ((size_t)width * height >= ((size_t)1 << 30)) return fail(SGMB_E_UNSUPPORTED, "image too large");
+
+    c->opt = *option;
+    c->W = width; c->H = height; c->D = D;
+    c->N = (size_t)width * height;
+    c->NR = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
+    c->Dp = (D + 15) & ~15;
+    c->nDirs = (option->num_paths == 4) ? 4 : 8;      // the reference ignores num_paths (always 8)
+    c->padF = ((option->min_disparity + 64 * c->NR + 8) + 3) & ~3;
+    c->copyStride = ((size_t)c->padF + c->N + 16 + 3) & ~(size_t)3;
+    c->planeStride = c->N * (size_t)c->Dp;
+    const int W = c->W, H = c->H;
+
+    // ---- K3 launch shape
+    const size_t smemMax = 227 * 1024;
+    c->wtaTW = 0;
+    for (int tw : {128, 64, 32}) {
+        const size_t need = wta_smem_bytes(tw, D, c->Dp, W);
+        if ((tw == 128 && need <= 110 * 1024) || (tw != 128 && need <= smemMax)) { c->wtaTW = tw; c->wtaSmem = need; break; }
+    }
+    if (!c->wtaTW) return fail(SGMB_E_UNSUPPORTED, "image row too wide for the WTA kernel's shared memory");
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
+
+    // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel)
+    std::vector<PathWork> irregular, regular;
+    std::vector<int32_t> entryOf(c->N, -1);
+    int nEntries = 0;
+    auto push_dir = [&](int d, int npaths) {
+        for (int i = 0; i < npaths; ++i) regular.push_back(PathWork{i, (uint8_t)d, 0, 0});
+    };
+    // longest paths first: the horizontal directions have only H warps of W steps each
+    if (W >= H) { push_dir(0, H); push_dir(1, H); push_dir(2, W); push_dir(3, W); }
+    else        { push_dir(2, W); push_dir(3, W); push_dir(0, H); push_dir(1, H); }
+    for (int d = 4; d < c->nDirs; ++d) {
+        const Dir dir = direction(d);
+        for (int i = 0; i < W; ++i) {
+            if (path_is_regular(W, H, d, i)) { regular.push_back(PathWork{i, (uint8_t)d, 0, 0}); continue; }
+            irregular.push_back(PathWork{i, (uint8_t)d, 1, 0});
+            PathWalker wk;
+            wk.start(W, H, dir.dx, dir.dy, i);
+            for (int s = 0; s < H; ++s) {
+                if (s) wk.advance();
+                if (wk.inside() && entryOf[wk.pos] < 0) entryOf[wk.pos] = nEntries++;
+            }
+        }
+    }
+    std::vector<PathWork> work(irregular);
+    work.insert(work.end(), regular.begin(), regular.end());
+    c->nWork = (int)work.size();
+    c->nEntries = nEntries;
+    c->nIrregular = (int)irregular.size();
+    CU(cudaMalloc(&c->work, work.size() * sizeof(PathWork)));
+    CU(cudaMemcpy(c->work, work.data(), work.size() * sizeof(PathWork), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->entryOf, c->N * sizeof(int32_t)));
+    CU(cudaMemcpy(c->entryOf, entryOf.data(), c->N * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+    // ---- penalty table: min(256, max(P1, P2_init / (delta + 1)))  (SemiGlobalMatching.c:335); candidates above
+    //      255 can never be selected, so clamping at 256 keeps the 16-bit fields from overflowing
+    uint16_t tab[256];
+    for (int dg = 0; dg < 256; ++dg) tab[dg] = (uint16_t)std::min(256, std::max((int)option->p1, (int)option->p2_init / (dg + 1)));
+    c->p1c = std::min(256, (int)option->p1);
+    CU(cudaMalloc(&c->p2tab, sizeof tab));
+    CU(cudaMemcpy(c->p2tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+
+    // ---- per-slot device buffers
+    for (auto& s : c->slots) {
+        CU(cudaMalloc(&s.img[0], c->N + 16)); CU(cudaMalloc(&s.img[1], c->N + 16));
+        CU(cudaMalloc(&s.censusL, c->N * sizeof(uint32_t)));
+        CU(cudaMalloc(&s.censusR4, 4 * c->copyStride * sizeof(uint32_t)));
+        CU(cudaMemset(s.censusR4, 0, 4 * c->copyStride * sizeof(uint32_t)));
+        CU(cudaMalloc(&s.planes, (size_t)c->nDirs * c->planeStride));
+        // slots on an irregular path's toroidal diagonal are never written by K2 and must read as 0 in K3
+        CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
+        CU(cudaMalloc(&s.side, std::max<size_t>(1, (size_t)nEntries) * c->Dp * sizeof(uint16_t) + 64));
+        CU(cudaMalloc(&s.dispLR, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.dispSpeckle, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.dispFinal, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.labels, 2 * c->N * sizeof(int32_t)));
+        const size_t xbytes = (size_t)((H + 31) / 32) * W * sizeof(unsigned long long);
+        CU(cudaMalloc(&s.xchg, xbytes));
+        CU(cudaMemset(s.xchg, 0, xbytes));
+        s.medianEpoch = 0;
+        s.busy = false;
+    }
+    if (c->pipeline & SGMB_PIPE_TAPS) if (int rc = alloc_taps(c)) return rc;
+    CU(cudaDeviceSynchronize());
+    c->configured = true;
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_SetPipeline(SGMB_Context* c, unsigned flags)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    c->pipeline = flags;
+    if (c->configured && (flags & SGMB_PIPE_TAPS)) {
+        if (int rc = ensure_device(c)) return rc;
+        return alloc_taps(c);
+    }
+    return SGMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one frame
+// Enqueue the whole pipeline on the slot's stream.  dL/dR: device images; result left in slot.dispFinal
+// (or dOut when given).  Returns the number of kernels launched through *launches.
+static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint8_t* dR, float* dOut, bool timeAgg, int* launches)
+{
+    const int W = c->W, H = c->H, D = c->D;
+    const bool taps = (c->pipeline & SGMB_PIPE_TAPS) != 0;
+    const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
+    const bool doMedian = (c->pipeline & SGMB_PIPE_MEDIAN) != 0;
+    int nk = 0;
+
+    if (c->nEntries > 0) CU(cudaMemsetAsync(s.side, 0, (size_t)c->nEntries * c->Dp * sizeof(uint16_t), s.stream));
+
+    {   // K1 census
+        CensusParams p{};
+        p.img[0] = dL; p.img[1] = dR; p.left = s.censusL; p.right4 = s.censusR4;
+        p.copyStride = c->copyStride; p.padF = c->padF; p.W = W; p.H = H;
+        dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
+        sgm_census5x5<<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
+        ++nk;
+    }
+    {   // K2 aggregation
+        AggParams p{};
+        p.img = dL; p.censusL = s.censusL; p.censusR4 = s.censusR4; p.copyStride = c->copyStride; p.padF = c->padF;
+        p.planes = s.planes; p.planeStride = c->planeStride; p.side = reinterpret_cast<uint32_t*>(s.side);
+        p.entryOf = c->entryOf; p.p2tab = c->p2tab; p.work = c->work; p.nWork = c->nWork;
+        p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity; p.p1 = c->p1c;
+        const int blocks = (c->nWork + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
+        if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
+        if (c->NR == 1)      sgm_aggregate_paths<1><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
+        else if (c->NR == 2) sgm_aggregate_paths<2><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
+        else                 sgm_aggregate_paths<4><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
+        if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
+        ++nk;
+    }
+    float* lrOut = s.dispLR;
+    {   // K3 plane sum + WTA + LR
+        WtaParams p{};
+        p.planes = s.planes; p.planeStride = c->planeStride; p.nPlanes = c->nDirs;
+        p.side = s.side; p.entryOf = c->entryOf; p.hasSide = c->nEntries > 0;
+        p.S = taps ? s.S : nullptr; p.dispLeftWta = taps ? s.dispLeftWta : nullptr; p.dispRight = taps ? s.dispRight : nullptr;
+        p.dispOut = lrOut;
+        p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity;
+        p.checkUnique = c->opt.is_check_unique; p.oneMinusRatio = 1 - c->opt.uniqueness_ratio;
+        p.checkLR = c->opt.is_check_lr; p.lrThres = c->opt.lrcheck_thres;
+        p.ringCols = c->wtaTW + D;
+        if (c->wtaTW == 128)     sgm_reduce_wta_lr<128><<<H, 256, c->wtaSmem, s.stream>>>(p);
+        else if (c->wtaTW == 64) sgm_reduce_wta_lr<64><<<H, 128, c->wtaSmem, s.stream>>>(p);
+        else                     sgm_reduce_wta_lr<32><<<H, 64, c->wtaSmem, s.stream>>>(p);
+        ++nk;
+    }
+    float* cur = lrOut;
+    if (doSpeckle) {
+        float* out = s.dispSpeckle;
+        nk += launch_speckle_filter(cur, out, s.labels, W, H, 1.0f, c->opt.min_speckle_area, s.stream);
+        cur = out;
+    }
+    if (doMedian) {
+        float* out = s.dispFinal;
+        nk += launch_median3_inplace(cur, out, s.xchg, &s.medianEpoch, W, H, s.stream);
+        cur = out;
+    }
+    if (dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaGetLastError());
+    if (launches) *launches = nk;
+    return SGMB_OK;
+}
+
+static float* frame_result(SGMB_Context* c, Slot& s)
+{
+    const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
+    const bool doMedian = (c->pipeline & SGMB_PIPE_MEDIAN) != 0;
+    return doMedian ? s.dispFinal : (doSpeckle ? s.dispSpeckle : s.dispLR);
+}
+
+extern "C" int SGMB_Match(SGMB_Context* c, const uint8_t* L, const uint8_t* R, float* out)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_Match: context is not configured");   // SemiGlobalMatching.c:70-72
+    if (!L || !R) return fail(SGMB_E_ARG, "SGMB_Match: NULL image");                                 // SemiGlobalMatching.c:73-75
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    CU(cudaEventRecord(s.evStart, s.stream));
+    CU(cudaMemcpyAsync(s.img[0], L, c->N, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.img[1], R, c->N, cudaMemcpyHostToDevice, s.stream));
+    if (int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr)) return rc;
+    if (out) CU(cudaMemcpyAsync(out, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaEventRecord(s.evStop, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_MatchDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int sync)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_MatchDevice: context is not configured");
+    if (!dL || !dR || !dOut) return fail(SGMB_E_ARG, "SGMB_MatchDevice: NULL pointer");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    CU(cudaEventRecord(s.evStart, s.stream));
+    if (int rc = enqueue_frame(c, s, dL, dR, dOut, false, nullptr)) return rc;
+    CU(cudaEventRecord(s.evStop, s.stream));
+    if (sync) {
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+    }
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_Synchronize(SGMB_Context* c)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if (int rc = ensure_device(c)) return rc;
+    for (auto& s : c->slots) CU(cudaStreamSynchronize(s.stream));
+    return SGMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+static int run_batch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* const* Rs, float* const* outs, int n, bool deviceMem)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "batch: context is not configured");
+    if (n < 0 || (n > 0 && (!Ls || !Rs || !outs))) return fail(SGMB_E_ARG, "batch: bad arguments");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s0 = c->slots[0];
+    CU(cudaEventRecord(s0.evStart, s0.stream));
+    for (int k = 0; k < n; ++k) {
+        if (!Ls[k] || !Rs[k] || !outs[k]) return fail(SGMB_E_ARG, "batch: NULL pointer at pair %d", k);
+        Slot& s = c->slots[k % c->nslots];
+        if (k == 0) { for (int j = 1; j < c->nslots; ++j) CU(cudaStreamWaitEvent(c->slots[j].stream, s0.evStart, 0)); }
+        if (deviceMem) {
+            if (int rc = enqueue_frame(c, s, Ls[k], Rs[k], outs[k], false, nullptr)) return rc;
+        } else {
+            CU(cudaMemcpyAsync(s.img[0], Ls[k], c->N, cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.img[1], Rs[k], c->N, cudaMemcpyHostToDevice, s.stream));
+            if (int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr)) return rc;
+            CU(cudaMemcpyAsync(outs[k], frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    for (int j = 1; j < c->nslots; ++j) {
+        CU(cudaEventRecord(c->slots[j].evDone, c->slots[j].stream));
+        CU(cudaStreamWaitEvent(s0.stream, c->slots[j].evDone, 0));
+    }
+    CU(cudaEventRecord(s0.evStop, s0.stream));
+    CU(cudaStreamSynchronize(s0.stream));
+    CU(cudaEventElapsedTime(&c->lastMs, s0.evStart, s0.evStop));
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_MatchBatch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* const* Rs, float* const* outs, int n)
+{
+    return run_batch(c, Ls, Rs, outs, n, false);
+}
+
+extern "C" int SGMB_MatchBatchDevice(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* const* Rs, float* const* outs, int n)
+{
+    return run_batch(c, Ls, Rs, outs, n, true);
+}
+
+extern "C" int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots, uint16_t width, uint16_t height,
+                                       const SGMOption* option, unsigned flags, const uint8_t* const* Ls,
+                                       const uint8_t* const* Rs, float* const* outs, int n)
+{
+    if (!devices || ndev < 1 || n < 0 || !option) return fail(SGMB_E_ARG, "SGMB_MatchBatchMultiGPU: bad arguments");
+    std::vector<int> rcs(ndev, SGMB_OK);
+    std::vector<std::string> msgs(ndev);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ndev; ++g) {
+        th.emplace_back([&, g]() {
+            const int lo = (int)((long long)n * g / ndev), hi = (int)((long long)n * (g + 1) / ndev);   // contiguous shard
+            SGMB_Context* ctx = nullptr;
+            int rc = SGMB_Create(&ctx, devices[g], slots);
+            if (!rc) rc = SGMB_SetPipeline(ctx, flags);
+            if (!rc) rc = SGMB_Configure(ctx, width, height, option);
+            if (!rc && hi > lo) rc = SGMB_MatchBatch(ctx, Ls + lo, Rs + lo, outs + lo, hi - lo);
+            if (rc) msgs[g] = g_err;
+            rcs[g] = rc;
+            SGMB_Destroy(ctx);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < ndev; ++g)
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", devices[g], msgs[g].c_str());
+    return SGMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ taps
+extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_GetStage: context is not configured");
+    if (!dst) return fail(SGMB_E_ARG, "SGMB_GetStage: NULL destination");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    CU(cudaStreamSynchronize(s.stream));
+    const size_t N = c->N;
+    const bool taps = c->tapsAllocated && (c->pipeline & SGMB_PIPE_TAPS);
+    const void* src = nullptr;
+    size_t need = 0;
+    switch (stage) {
+        case SGMB_STAGE_CENSUS_LEFT:   src = s.censusL; need = N * 4; break;
+        case SGMB_STAGE_CENSUS_RIGHT:  src = s.censusR4 + c->padF; need = N * 4; break;   // copy 0 is unshifted
+        case SGMB_STAGE_AGGR:          src = taps ? s.S : nullptr; need = N * c->D * 2; break;
+        case SGMB_STAGE_DISP_LEFT_WTA: src = taps ? s.dispLeftWta : nullptr; need = N * 4; break;
+        case SGMB_STAGE_DISP_RIGHT:    src = taps ? s.dispRight : nullptr; need = N * 4; break;
+        case SGMB_STAGE_DISP_LR:       src = s.dispLR; need = N * 4; break;
+        case SGMB_STAGE_DISP_SPECKLE:  src = ((c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles) ? s.dispSpeckle : s.dispLR; need = N * 4; break;
+        case SGMB_STAGE_DISP_FINAL:    src = frame_result(c, s); need = N * 4; break;
+        default:
+            if (stage >= SGMB_STAGE_PATH_PLANE_0 && stage < SGMB_STAGE_PATH_PLANE_0 + c->nDirs) {
+                need = N * c->D;
+                if (bytes != need) return fail(SGMB_E_STATE, "SGMB_GetStage: stage %d needs %zu bytes, got %zu", stage, need, bytes);
+                const uint8_t* plane = s.planes + (size_t)(stage - SGMB_STAGE_PATH_PLANE_0) * c->planeStride;
+                CU(cudaMemcpy2D(dst, c->D, plane, c->Dp, c->D, N, cudaMemcpyDeviceToHost));
+                return SGMB_OK;
+            }
+            return fail(SGMB_E_ARG, "SGMB_GetStage: unknown stage %d", stage);
+    }
+    if (!src) return fail(SGMB_E_STATE, "SGMB_GetStage: stage %d is only retained with SGMB_PIPE_TAPS", stage);
+    if (bytes != need) return fail(SGMB_E_STATE, "SGMB_GetStage: stage %d needs %zu bytes, got %zu", stage, need, bytes);
+    CU(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_HostAlloc(void** out, size_t bytes)
+{
+    if (!out) return fail(SGMB_E_ARG, "NULL");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return SGMB_OK;
+}
+
+extern "C" void SGMB_HostFree(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------ introspection
+extern "C" int SGMB_KernelLaunchesPerFrame(SGMB_Context* c)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "not configured");
+    const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
+    const bool doMedian = (c->pipeline & SGMB_PIPE_MEDIAN) != 0;
+    return 3 + (doSpeckle ? kSpeckleLaunches : 0) + (doMedian ? kMedianLaunches : 0);
+}
+
+extern "C" double SGMB_ModelBytesPerFrame(SGMB_Context* c)
+{
+    if (!c || !c->configured) return 0.0;
+    return (double)c->N * (4.0 * c->nDirs * c->D + 6.0);
+}
+
+extern "C" double SGMB_PlanBytesPerFrame(SGMB_Context* c)
+{
+    if (!c || !c->configured) return 0.0;
+    // planes written once by K2 and read once by K3 (Dp bytes per pixel and direction), census/images/disparity per pixel
+    return (double)c->N * (2.0 * c->nDirs * c->Dp + 2 + 4 + 4 * 4 + 4 * 4 + 4);
+}
+
+extern "C" float SGMB_LastDeviceMs(SGMB_Context* c) { return c ? c->lastMs : -1.f; }
+
+__global__ void sgm_flush_l2(uint4* buf, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = make_uint4(i, 0, 0, 0);
+}
+
+extern "C" int SGMB_TimeDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int warmup, int iters,
+                               int flush_l2, float* frame_ms, float* agg_ms)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_TimeDevice: context is not configured");
+    if (!dL || !dR || !dOut || iters < 1 || warmup < 0) return fail(SGMB_E_ARG, "SGMB_TimeDevice: bad arguments");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    if (flush_l2 && !c->flushBuf) {
+        c->flushBytes = (size_t)256 << 20;   // 2x the 126 MB L2
+        CU(cudaMalloc(&c->flushBuf, c->flushBytes));
+    }
+    for (int it = -warmup; it < iters; ++it) {
+        if (flush_l2) sgm_flush_l2<<<148 * 8, 256, 0, s.stream>>>(reinterpret_cast<uint4*>(c->flushBuf), c->flushBytes / 16);
+        CU(cudaEventRecord(s.evStart, s.stream));
+        if (int rc = enqueue_frame(c, s, dL, dR, dOut, true, nullptr)) return rc;
+        CU(cudaEventRecord(s.evStop, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        if (it >= 0) {
+            if (frame_ms) CU(cudaEventElapsedTime(&frame_ms[it], s.evStart, s.evStop));
+            if (agg_ms) CU(cudaEventElapsedTime(&agg_ms[it], s.evAgg0, s.evAgg1));
+        }
+    }
+    return SGMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ reference API
+static SGMB_Context* g_ctx = nullptr;
+static int g_device = -1;
+static std::mutex g_mu;
+
+extern "C" SGMB_Context* SGMB_GlobalContext(void) { return g_ctx; }
+
+extern "C" int SGMB_SetGlobalDevice(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx && g_ctx->device != device) { SGMB_Destroy(g_ctx); g_ctx = nullptr; }
+    g_device = device;
+    return SGMB_OK;
+}
+
+// replaces SemiGlobalMatching.c:37-66
+extern "C" bool SGM_Initialize(uint16_t width, uint16_t height, const SGMOption* option)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!option) { fail(SGMB_E_ARG, "SGM_Initialize: NULL option"); return false; }
+    if (!g_ctx) {
+        int dev = g_device;
+        if (dev < 0) { const char* e = getenv("SGM_B200_DEVICE"); dev = e ? atoi(e) : 0; }
+        if (SGMB_Create(&g_ctx, dev, 1) != SGMB_OK) { g_ctx = nullptr; return false; }
+    }
+    return SGMB_Configure(g_ctx, width, height, option) == SGMB_OK;
+}
+
+// replaces SemiGlobalMatching.c:128-132
+extern "C" bool SGM_Reset(uint16_t width, uint16_t height, const SGMOption* option)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_ctx) g_ctx->configured = false;
+    }
+    return SGM_Initialize(width, height, option);
+}
+
+// replaces SemiGlobalMatching.c:68-125
+extern "C" bool SGM_Match(const uint8_t* img_left, const uint8_t* img_right, float* disp_left)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) { fail(SGMB_E_STATE, "SGM_Match: SGM_Initialize has not succeeded"); return false; }
+    return SGMB_Match(g_ctx, img_left, img_right, disp_left) == SGMB_OK;
+}
