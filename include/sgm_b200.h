@@ -110,6 +110,12 @@ float  SGMB_LastDeviceMs(SGMB_Context* ctx);
 int SGMB_TimeDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int warmup,
                     int iters, int flush_l2, float* frame_ms, float* aggr_kernel_ms);
 
+/* Enqueue `iters` device-resident frames back to back on slot 0 without host synchronisation and time the
+ * whole region with CUDA events on that stream (*total_ms); agg_ms (optional, [iters]) receives the duration
+ * of every aggregation-kernel launch inside the region. */
+int SGMB_RunDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int iters,
+                   float* total_ms, float* agg_ms);
+
 /* The context behind SGM_Initialize/SGM_Match (NULL before the first SGM_Initialize), and the device it
  * will use (default 0, or env SGM_B200_DEVICE). */
 SGMB_Context* SGMB_GlobalContext(void);

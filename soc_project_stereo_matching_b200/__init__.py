@@ -17,7 +17,6 @@ import os
 
 import numpy as np
 
-from . import build as _build
 
 __all__ = ["SGMOption", "SGM_Initialize", "SGM_Reset", "SGM_Match", "Context", "lib", "last_error",
            "default_option", "INVALID_FLOAT", "PIPE_SPECKLE", "PIPE_MEDIAN", "PIPE_TAPS", "PIPE_REFERENCE",
@@ -57,6 +56,7 @@ def default_option(**kw) -> SGMOption:
 
 
 def _load() -> C.CDLL:
+    from . import build as _build      # imported lazily so `python -m <package>.build` runs cleanly
     path = _build.LIB
     if not os.path.isfile(path):
         raise ImportError(
@@ -88,6 +88,7 @@ def _load() -> C.CDLL:
         "SGMB_PlanBytesPerFrame": (C.c_double, [vp]),
         "SGMB_LastDeviceMs": (C.c_float, [vp]),
         "SGMB_TimeDevice": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+        "SGMB_RunDevice": (i32, [vp, vp, vp, vp, i32, vp, vp]),
         "SGMB_GlobalContext": (vp, []),
         "SGMB_SetGlobalDevice": (i32, [i32]),
         "SGMB_DebugWalkPath": (i32, [i32, i32, i32, i32, vp, i32]),
@@ -274,6 +275,15 @@ class Context:
         frame = np.zeros(iters, np.float32); agg = np.zeros(iters, np.float32)
         _check(lib.SGMB_TimeDevice(self._h, d_left, d_right, d_out, warmup, iters, int(flush_l2), frame.ctypes.data, agg.ctypes.data))
         return frame, agg
+
+
+    def run_device(self, d_left: int, d_right: int, d_out: int, iters: int, time_aggregation: bool = True):
+        """-> (total milliseconds of `iters` back-to-back frames, per-launch aggregation-kernel ms)."""
+        total = C.c_float(0)
+        agg = np.zeros(iters, np.float32)
+        _check(lib.SGMB_RunDevice(self._h, d_left, d_right, d_out, iters, C.byref(total),
+                                  agg.ctypes.data if time_aggregation else None))
+        return float(total.value), agg
 
 
 def match_batch_multi_gpu(devices, slots_per_device, width, height, option, pipeline, lefts, rights) -> np.ndarray:

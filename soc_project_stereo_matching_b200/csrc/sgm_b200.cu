@@ -629,6 +629,39 @@ extern "C" int SGMB_TimeDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t
     return SGMB_OK;
 }
 
+// Enqueue `iters` frames back to back on slot 0 (device-resident input and output, no host synchronisation in
+// between) and time the whole region with CUDA events on that stream; optionally also every aggregation launch.
+extern "C" int SGMB_RunDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int iters,
+                              float* total_ms, float* agg_ms /* [iters] or NULL */)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_RunDevice: context is not configured");
+    if (!dL || !dR || !dOut || iters < 1) return fail(SGMB_E_ARG, "SGMB_RunDevice: bad arguments");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    std::vector<cudaEvent_t> ev;
+    if (agg_ms) {
+        ev.resize(2 * (size_t)iters);
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+    }
+    cudaEvent_t keep0 = s.evAgg0, keep1 = s.evAgg1;
+    CU(cudaEventRecord(s.evStart, s.stream));
+    int rc = SGMB_OK;
+    for (int it = 0; it < iters && rc == SGMB_OK; ++it) {
+        if (agg_ms) { s.evAgg0 = ev[2 * it]; s.evAgg1 = ev[2 * it + 1]; }
+        rc = enqueue_frame(c, s, dL, dR, dOut, agg_ms != nullptr, nullptr);
+    }
+    s.evAgg0 = keep0; s.evAgg1 = keep1;
+    if (rc == SGMB_OK) {
+        CU(cudaEventRecord(s.evStop, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+        if (total_ms) *total_ms = c->lastMs;
+        if (agg_ms) for (int it = 0; it < iters; ++it) CU(cudaEventElapsedTime(&agg_ms[it], ev[2 * it], ev[2 * it + 1]));
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ reference API
 static SGMB_Context* g_ctx = nullptr;
 static int g_device = -1;
