@@ -1,4 +1,4 @@
-// aggregate.cuh -- K2: multi-path cost aggregation, one warp per path, disparities across lanes.
+// aggregate.cuh -- K2: multi-path cost aggregation; disparities across lanes, path state in registers.
 //
 // Restates CostAggregate() (SemiGlobalMatching.c:229-372) with the matching cost of ComputeCost()/
 // Hamming32() (SemiGlobalMatching.c:161-196) computed on the fly as popc(xor), so C(p,d) is never
@@ -8,19 +8,27 @@
 //                                              minPrev + max(P1, P2_init/(|g-gPrev|+1))) - minPrev )
 //                            with Lp[-1] = Lp[D] = 255, uint16 candidates, wrap mod 256  (:325-353)
 //
-// Mapping: lane l owns the 2*NR consecutive disparity indices [2*NR*l, 2*NR*(l+1)) as NR registers of
-// two 16-bit fields (index 2r in the low half of register r).  The 16-bit fields make every DP step a
-// native DPX instruction (VIADDMNMX.U16x2 / VIMNMX.U16x2; the 8-bit SIMD intrinsics __vminu4/__vaddus4
-// are emulated with 5-8 ALU ops each on sm_100a) while values stay <= 255, so the reference's mod-256
-// wrap is one AND.  Lp[d-1]/Lp[d+1] across lane edges come from __shfl_up_sync/__shfl_down_sync, min_d
-// from __reduce_min_sync; all path state lives in registers.  Candidates are allowed to exceed 255
-// (they can never win against Lp[d] <= 255), only the final C + m - minPrev is wrapped.
+// Mapping: a path is owned by a group of LPP lanes (32, 16 or 8); lane s of the group owns the 2*NR
+// consecutive disparity indices [2*NR*s, 2*NR*(s+1)) as NR registers of two 16-bit fields (index 2r in
+// the low half of register r).  16-bit fields make every DP step a native DPX instruction
+// (VIADDMNMX.U16x2 / VIMNMX.U16x2; the 8-bit SIMD intrinsics __vminu4/__vaddus4 are emulated with 5-8
+// ALU ops each on sm_100a) while values stay <= 255, so the reference's mod-256 wrap is one AND.
+// Lp[d-1]/Lp[d+1] across lane edges come from __shfl_up_sync/__shfl_down_sync, min_d from
+// __reduce_min_sync (LPP == 32) or a shuffle butterfly; all path state lives in registers.  Candidates may
+// exceed 255 (they can never win against Lp[d] <= 255); only the final C + m - minPrev is wrapped.
 //
-// Output: each direction r owns a uint8 plane [N][Dp]; the warp stores L_r(p, .) with one 64*NR-byte
-// coalesced store per pixel.  No direction reads or modifies another one's data, so all directions
-// run concurrently in ONE launch without atomics; K3 sums the planes into the uint16 S while it
-// computes the disparities.  Paths flagged irregular (the reference's anomalous diagonal walks, which
-// visit some pixels twice) add their L into a small uint16 side buffer addressed through entryOf[].
+// The kernel is bound by instruction issue, not by HBM (ncu: profiles/), so the per-step overhead that
+// does not depend on the number of disparities (position update, the three loads, penalty lookup, the two
+// shuffles, the min reduction, the store) is amortised by giving each lane MORE disparities and putting
+// 32/LPP paths of the same direction in one warp.  The horizontal directions have only H paths of W steps
+// each and are the latency-critical ones, so they keep more lanes per path.
+//
+// Output: each direction r owns a uint8 plane [N][Dp]; a group stores L_r(p, .) with one coalesced store
+// per pixel.  No direction reads or modifies another one's data, so all directions run concurrently in ONE
+// launch without atomics; K3 sums the planes into the uint16 S while it computes the disparities.  Paths
+// flagged irregular (the reference's anomalous diagonal walks, which visit some pixels twice and are
+// followed with the generic walker of path_walker.h) add their L into a small uint16 side buffer addressed
+// through entryOf[].
 #pragma once
 
 #include <stdint.h>
@@ -28,10 +36,10 @@
 
 namespace sgmb {
 
-struct PathWork {           // one warp's job
-    int path;               // path index inside its direction
+struct WarpWork {           // one warp's job
+    int firstPath;          // first path index inside its direction
     uint8_t dir;            // 0..7, order of SemiGlobalMatching.c:213-220
-    uint8_t irregular;      // 1: walk leaves the toroidal diagonal -> results go to the side buffer
+    uint8_t count;          // paths handled by this warp (<= 32 / LPP; 1 for irregular paths)
     uint16_t pad;
 };
 
@@ -39,43 +47,41 @@ struct AggParams {
     const uint8_t* img;         // left image [N]
     const uint32_t* censusL;    // [N]
     const uint32_t* censusR4;   // [4][copyStride], see census.cuh
-    size_t copyStride;
+    uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
     uint8_t* planes;            // [8][planeStride]
     size_t planeStride;         // bytes per plane = N * Dp
     uint32_t* side;             // uint16 [E][Dp] viewed as packed pairs, zeroed per frame
     const int32_t* entryOf;     // [N] -> side-buffer entry or -1
-    const uint16_t* p2tab;      // [256] min(256, max(P1, P2_init/(delta+1)))
-    const PathWork* work;
-    int nWork;
+    const WarpWork* work;       // [nIrregularWarps] irregular jobs, then [nRegularWarps] regular jobs
+    int nIrregularWarps, nRegularWarps;
     int W, H, D, Dp, dmin;
-    int p1;                     // min(P1, 256)
+    uint32_t p1x2;              // min(P1, 256) in both 16-bit fields
+    uint32_t p2x2[256];         // min(256, max(P1, P2_init/(delta+1))) in both fields, indexed by |g - gPrev|
 };
 
 constexpr int kAggWarpsPerBlock = 4;
 
+// ------------------------------------------------------------------------------------------------ shared pieces
 template <int NR>
 struct StepInput {
     uint32_t v[2 * NR];   // right census descriptors: v[j] = cR[q_top - (2*NR-1) + j]
     uint32_t cl;          // left census descriptor of the pixel
     uint32_t g;           // grey value of the pixel
-    int pos, tcol;
-    bool inside;
 };
 
+// Loads of one pixel visit: grey value, left descriptor and the window cR[q_top-(DPL-1) .. q_top] with
+// q_top = pos - dmin - DPL*sub, fetched from the copy that makes the window 8/16-byte aligned.
 template <int NR>
-__device__ __forceinline__ void load_step(const AggParams& P, const PathWalker& wk, int lane, StepInput<NR>& in)
+__device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int sub, StepInput<NR>& in)
 {
     constexpr int DPL = 2 * NR;
     constexpr int VEC = DPL < 4 ? DPL : 4;
-    in.pos = wk.pos; in.tcol = wk.tcol; in.inside = wk.inside();
-    if (!in.inside) return;
-    in.g = __ldg(P.img + wk.pos);
-    in.cl = __ldg(P.censusL + wk.pos);
-    // window cR[q_top-(DPL-1) .. q_top], q_top = pos - dmin - DPL*lane, fetched from the copy that makes it aligned
-    const int y0 = wk.pos - P.dmin - DPL * lane - (DPL - 1) + P.padF;
-    const int a = (-y0) & (VEC - 1);
-    const uint32_t* src = P.censusR4 + (size_t)a * P.copyStride + (y0 + a);
+    in.g = __ldg(P.img + pos);
+    in.cl = __ldg(P.censusL + pos);
+    const uint32_t y0 = pos - (uint32_t)(P.dmin + DPL * sub + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
+    const uint32_t al = (y0 + (VEC - 1)) & ~(uint32_t)(VEC - 1);
+    const uint32_t* src = P.censusR4 + ((al - y0) * P.copyStride + al);
     if (VEC == 2) {
         const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
         in.v[0] = t.x; in.v[1] = t.y;
@@ -88,132 +94,439 @@ __device__ __forceinline__ void load_step(const AggParams& P, const PathWalker& 
     }
 }
 
+// Matching cost of the lane's 2*NR disparities, packed two per register (SemiGlobalMatching.c:170-177).
+// BORDER: the pixel is so close to the left image edge that some right columns are negative -> cost 127
+// for disparity indices >= nvalid.
+template <int NR, bool BORDER>
+__device__ __forceinline__ void pack_cost(const StepInput<NR>& in, int nvalid, uint32_t (&C)[NR])
+{
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        uint32_t c0 = __popc(in.cl ^ in.v[2 * NR - 1 - 2 * r]);
+        uint32_t c1 = __popc(in.cl ^ in.v[2 * NR - 2 - 2 * r]);
+        if (BORDER) {
+            c0 = (2 * r < nvalid) ? c0 : 127u;
+            c1 = (2 * r + 1 < nvalid) ? c1 : 127u;
+        }
+        C[r] = c1 * 65536u + c0;
+    }
+}
+
+// One DP step on the lane's registers.  up / dn: the neighbouring lanes' edge registers (sentinel 0x00FF00FF
+// at the ends of the disparity range).
 template <int NR>
-__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
-sgm_aggregate_paths(AggParams P)
+__device__ __forceinline__ void dp_step(uint32_t (&L)[NR], const uint32_t (&C)[NR], const uint32_t (&padm)[NR],
+                                        uint32_t up, uint32_t dn, uint32_t p1x2, uint32_t p2x2, uint32_t negmin)
+{
+    uint32_t lm1 = __byte_perm(up, L[0], 0x5432);                          // Lp[d-1] of both fields of register 0
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const uint32_t above = (r == NR - 1) ? dn : L[r + 1];
+        const uint32_t lp1 = __byte_perm(L[r], above, 0x5432);             // Lp[d+1]; also Lp[d-1] of register r+1
+        uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[r]);                    // min(Lp[d-1]+P1, Lp[d])
+        t = __viaddmin_u16x2(lp1, p1x2, t);                                // min(Lp[d+1]+P1, .)
+        t = __viaddmin_u16x2(t, negmin, p2x2);                             // min(. - minPrev, P2')   in [0, 255]
+        L[r] = (__vadd2(C[r], t) & 0x00FF00FFu) | padm[r];                 // (uint8)(C + m - minPrev)
+        lm1 = lp1;
+    }
+}
+
+template <int NR>
+__device__ __forceinline__ uint32_t lane_min_x2(const uint32_t (&L)[NR])
+{
+    uint32_t m = L[0];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) m = __vminu2(m, L[r]);
+    return __vminu2(m, __byte_perm(m, 0, 0x1032));                         // both fields = min of the lane
+}
+
+template <int LPP>
+__device__ __forceinline__ uint32_t group_min_x2(uint32_t m)               // m: both fields equal
+{
+    if (LPP == 32) return __reduce_min_sync(0xffffffffu, m);
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+}
+
+template <int NR>
+__device__ __forceinline__ void store_plane(uint8_t* dst, const uint32_t (&L)[NR])
+{
+    if (NR == 1) {
+        __stcs(reinterpret_cast<unsigned short*>(dst), (unsigned short)__byte_perm(L[0], 0, 0x4420));
+    } else if (NR == 2) {
+        __stcs(reinterpret_cast<uint32_t*>(dst), __byte_perm(L[0], L[1], 0x6420));
+    } else if (NR == 4) {
+        __stcs(reinterpret_cast<uint2*>(dst), make_uint2(__byte_perm(L[0], L[1], 0x6420), __byte_perm(L[2], L[3], 0x6420)));
+    } else {
+#pragma unroll
+        for (int j = 0; j < NR / 8; ++j)
+            __stcs(reinterpret_cast<uint4*>(dst) + j, make_uint4(__byte_perm(L[8 * j + 0], L[8 * j + 1], 0x6420), __byte_perm(L[8 * j + 2], L[8 * j + 3], 0x6420),
+                                                          __byte_perm(L[8 * j + 4], L[8 * j + 5], 0x6420), __byte_perm(L[8 * j + 6], L[8 * j + 7], 0x6420)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ horizontal paths
+// One path (image row) per warp, 2*NR disparities per lane.  Only H paths exist per direction and each is W
+// dependent steps long, so this loop is latency-critical.  It contains NO global load and is software
+// pipelined: while the dependent chain of step s runs (shuffle -> DPX min/add -> warp min), the inputs of step
+// s+1 are prepared in the same basic block.
+//  * every 32 steps the warp fetches the next 32 pixels of the row with three coalesced loads (lane j holds the
+//    grey value, the left descriptor and the one new right descriptor of step 32b+1+j; fetched one block ahead)
+//    and every step broadcasts its pixel with __shfl_sync;
+//  * the right-census window cR[x-d] slides by one element per step, so it lives in registers and is shifted
+//    across lanes with one __shfl_up/down per step.
+template <int NR, bool FWD>
+struct HorizontalState {
+    uint32_t w[2 * NR];      // w[k] = cR[x - dmin - DPL*lane - k] for the column x being prepared
+    uint32_t L[NR];
+    uint32_t C[NR];          // cost of the prepared step
+    uint32_t p2x2;           // penalty of the prepared step
+    uint32_t g;              // grey value of the prepared step
+    uint32_t minx2;
+};
+
+// Prepare step with column x: broadcast its pixel from lane j of the block registers, slide the window, cost.
+template <int NR, bool FWD, bool BORDER>
+__device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD>& st, uint32_t gBlk, uint32_t clBlk,
+                                                   uint32_t crBlk, int j, int x, int lane, int dbase)
 {
     constexpr int DPL = 2 * NR;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ uint16_t s_p2[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_p2[i] = P.p2tab[i];
-    __syncthreads();
+    const uint32_t g = __shfl_sync(FULL, gBlk, j);
+    const uint32_t cl = __shfl_sync(FULL, clBlk, j);
+    const uint32_t fresh = __shfl_sync(FULL, crBlk, j);
+    if (FWD) {
+        uint32_t t = __shfl_up_sync(FULL, st.w[DPL - 1], 1);
+        if (lane == 0) t = fresh;
+#pragma unroll
+        for (int k = DPL - 1; k > 0; --k) st.w[k] = st.w[k - 1];
+        st.w[0] = t;
+    } else {
+        uint32_t t = __shfl_down_sync(FULL, st.w[0], 1);
+        if (lane == 31) t = fresh;
+#pragma unroll
+        for (int k = 0; k < DPL - 1; ++k) st.w[k] = st.w[k + 1];
+        st.w[DPL - 1] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        uint32_t c0 = __popc(cl ^ st.w[2 * r]);
+        uint32_t c1 = __popc(cl ^ st.w[2 * r + 1]);
+        if (BORDER) {                                   // right column x - d < 0  ->  cost 127 (SemiGlobalMatching.c:170-172)
+            c0 = (dbase + 2 * r <= x) ? c0 : 127u;
+            c1 = (dbase + 2 * r + 1 <= x) ? c1 : 127u;
+        }
+        st.C[r] = c1 * 65536u + c0;
+    }
+    int dg = (int)g - (int)st.g;
+    dg = dg < 0 ? -dg : dg;
+    st.p2x2 = P.p2x2[dg];
+    st.g = g;
+}
 
-    const int widx = blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
-    if (widx >= P.nWork) return;
-    const int lane = threadIdx.x & 31;
-    const PathWork job = P.work[widx];
-    const Dir dir = direction(job.dir);
+// n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
+// prepares the following step from lane i (when `more`).
+template <int NR, bool FWD, bool BORDER>
+__device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD>& st, const uint32_t (&padm)[NR], int n,
+                                                 int xnext, uint32_t gBlk, uint32_t clBlk, uint32_t crBlk, int lane, int dbase,
+                                                 uint8_t*& out, long long outStride, bool stores)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    for (int i = 0; i < n; ++i) {
+        // ---- dependent chain of the current step
+        uint32_t Ccur[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) Ccur[r] = st.C[r];
+        const uint32_t p2 = st.p2x2;
+        uint32_t up = __shfl_up_sync(FULL, st.L[NR - 1], 1);
+        uint32_t dn = __shfl_down_sync(FULL, st.L[0], 1);
+        if (lane == 0) up = 0x00FF00FFu;
+        if (lane == 31) dn = 0x00FF00FFu;
+        dp_step<NR>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
+        st.minx2 = group_min_x2<32>(lane_min_x2<NR>(st.L));
+        if (stores) store_plane<NR>(out, st.L);
+        out += outStride;
+        // ---- inputs of the next step (independent of the chain above)
+        horizontal_prepare<NR, FWD, BORDER>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, lane, dbase);
+    }
+}
 
-    // 0x00FF in every 16-bit field whose disparity index is >= D: those fields are pinned to 255, which is
-    // exactly the reference's Lp[D] = 255 sentinel (SemiGlobalMatching.c:260-263,357) for the last real d.
+template <int NR, bool FWD>
+__device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const WarpWork job, int lane)
+{
+    constexpr int DPL = 2 * NR;
+    const int W = P.W, row = job.firstPath;
+    const uint32_t rowBase = (uint32_t)row * (uint32_t)W;
+    const uint32_t* cR = P.censusR4 + P.padF;                       // copy 0: cR[p], zero padding in front
     uint32_t padm[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int i0 = DPL * lane + 2 * r;
         padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
     }
-    const uint32_t p1x2 = (uint32_t)P.p1 * 0x00010001u;
-    const int dbase = P.dmin + DPL * lane;              // absolute disparity of this lane's first index
-    const int dmax_warp = P.dmin + 64 * NR - 1;         // largest absolute disparity any lane may hold
+    const int dbase = P.dmin + DPL * lane;
+    const int dlast = P.dmin + 32 * DPL - 1;
+    const bool stores = DPL * lane < P.Dp;
+    const long long outStride = FWD ? (long long)P.Dp : -(long long)P.Dp;
+    uint8_t* out = P.planes + (size_t)job.dir * P.planeStride + ((size_t)rowBase + (FWD ? 0 : W - 1)) * P.Dp + DPL * lane;
 
-    uint8_t* plane = P.planes + (size_t)job.dir * P.planeStride;
+    auto column = [&](int s) { return FWD ? s : W - 1 - s; };
+    // block b holds steps 32*b+1 .. 32*b+32 (step 0 is set up below): lane j <-> step 32*b + 1 + j
+    auto load_block = [&](int b, uint32_t& gB, uint32_t& clB, uint32_t& crB) {
+        const int s = 32 * b + 1 + lane;
+        gB = 0; clB = 0; crB = 0;
+        if (s < W) {
+            const int x = column(s);
+            gB = __ldg(P.img + rowBase + x);
+            clB = __ldg(P.censusL + rowBase + x);
+            const int xin = FWD ? x - P.dmin : x - P.dmin - (32 * DPL - 1);   // element entering the window on arrival at x
+            if (xin >= 0) crB = __ldg(cR + rowBase + xin);
+        }
+    };
+
+    HorizontalState<NR, FWD> st;
+    uint32_t gA, clA, crA, gB, clB, crB;
+    load_block(0, gA, clA, crA);
+    // ---- step 0: window, cost, L = C (SemiGlobalMatching.c:266-275)
+    {
+        const int x0 = column(0);
+        const uint32_t cl = __ldg(P.censusL + rowBase + x0);
+        st.g = __ldg(P.img + rowBase + x0);
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+            const int xr = x0 - dbase - k;
+            st.w[k] = (xr >= 0) ? __ldg(cR + rowBase + xr) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t c0 = (dbase + 2 * r <= x0) ? __popc(cl ^ st.w[2 * r]) : 127u;
+            const uint32_t c1 = (dbase + 2 * r + 1 <= x0) ? __popc(cl ^ st.w[2 * r + 1]) : 127u;
+            st.L[r] = (c1 * 65536u + c0) | padm[r];
+        }
+        st.minx2 = group_min_x2<32>(lane_min_x2<NR>(st.L));
+        if (stores) store_plane<NR>(out, st.L);
+        out += outStride;
+    }
+    if (W == 1) return;
+    // prepare step 1 from lane 0 of block 0; afterwards every block iteration consumes one step and prepares the next
+    horizontal_prepare<NR, FWD, true>(P, st, gA, clA, crA, 0, column(1), lane, dbase);
+    // steps 1 .. W-1: step s is consumed in block (s-1)/32 at i = (s-1)%32, where step s+1 is prepared from lane i+1
+    // of the same block, or lane 0 of the next one.  To keep one loop body, rotate the block registers by one lane:
+    // consuming position i prepares from lane i of registers that hold steps 32*b+2 .. 32*b+33.
+    const int nsteps = W - 1;                                        // steps still to consume
+    int done = 0;
+    // registers for "prepare" lanes: lane j <-> step 32*b + 2 + j  == block registers shifted down by one lane
+    auto shifted = [&](uint32_t cur, uint32_t nxt) {
+        uint32_t v = __shfl_down_sync(0xffffffffu, cur, 1);
+        const uint32_t first = __shfl_sync(0xffffffffu, nxt, 0);
+        return lane == 31 ? first : v;
+    };
+    for (int b = 0; done < nsteps; ++b) {
+        load_block(b + 1, gB, clB, crB);                             // one block ahead
+        const uint32_t gS = shifted(gA, gB), clS = shifted(clA, clB), crS = shifted(crA, crB);
+        const int n = min(32, nsteps - done);                        // consume steps done+1 .. done+n, prepare done+2 .. done+n+1
+        const int sPrepFirst = done + 2;
+        const int xa = column(min(sPrepFirst, W - 1)), xb = column(min(sPrepFirst + n - 1, W - 1));
+        const bool border = min(xa, xb) < dlast;                     // warp-uniform
+        if (border) horizontal_block<NR, FWD, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, lane, dbase, out, outStride, stores);
+        else        horizontal_block<NR, FWD, false>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, lane, dbase, out, outStride, stores);
+        done += n;
+        gA = gB; clA = clB; crA = crB;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ vertical / diagonal paths
+// A regular vertical or diagonal path follows a column or the toroidal diagonal, so its position is updated
+// with a constant stride (plus one column wrap for diagonals); 32/LPP paths of one direction share a warp and
+// every lane owns 2*NR disparities.  The loads of visit s+1 are issued before the dependent chain of visit s
+// (two input buffers, loop unrolled by two).
+template <int NR, int LPP, bool DIAG>
+__device__ __forceinline__ void aggregate_column_like(const AggParams& P, const WarpWork job, int lane)
+{
+    static_assert(NR == 1 || NR == 2 || NR == 4 || NR == 8, "NR");
+    constexpr int DPL = 2 * NR;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int grp = lane / LPP, sub = lane % LPP;
+    const bool active = grp < (int)job.count;
+    const int path = job.firstPath + (active ? grp : (int)job.count - 1);      // idle groups shadow the last path
+
+    const Dir dir = direction(job.dir);
+    const bool fwd = dir.dy > 0;
+    const int W = P.W, H = P.H, len = H;
+    int tcol = path;
+    uint32_t pos = fwd ? (uint32_t)path : (uint32_t)((H - 1) * W + path);
+    const uint32_t dpos = (uint32_t)(dir.dy * W + dir.dx);
+    const int dcol = dir.dx;
+
+    uint32_t padm[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int i0 = DPL * sub + 2 * r;
+        padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
+    }
+    const int dbase = P.dmin + DPL * sub;                 // absolute disparity of this lane's first index
+    const int dlast = P.dmin + DPL * LPP - 1;             // largest absolute disparity the group may hold
+    const bool stores = active && (DPL * sub < P.Dp);
+    uint8_t* const planeLane = P.planes + (size_t)job.dir * P.planeStride + DPL * sub;
+    const uint32_t p1x2 = P.p1x2;
+    // vertical paths keep their column: whether the left image border matters is decided once per warp
+    const bool colBorder = DIAG ? false : (__any_sync(FULL, tcol < dlast) != 0);
+
+    uint32_t L[NR], C[NR];
+    uint32_t minx2, gPrev, posPrev;
+
+    auto advance = [&]() {
+        pos += dpos;
+        if (DIAG) {
+            tcol += dcol;
+            if (tcol >= W) { tcol -= W; pos -= (uint32_t)W; }
+            if (tcol < 0)  { tcol += W; pos += (uint32_t)W; }
+        }
+    };
+    auto cost = [&](const StepInput<NR>& in, int tc) {
+        const bool border = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
+        if (border) pack_cost<NR, true>(in, tc - dbase + 1, C);
+        else pack_cost<NR, false>(in, 0, C);
+    };
+    auto visit = [&](const StepInput<NR>& in, uint32_t p, int tc) {
+        cost(in, tc);
+        int dg = (int)in.g - (int)gPrev;
+        dg = dg < 0 ? -dg : dg;
+        gPrev = in.g;
+        const uint32_t p2x2 = P.p2x2[dg];
+        const uint32_t negmin = __vneg2(minx2);
+        uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1, LPP);
+        uint32_t dn = __shfl_down_sync(FULL, L[0], 1, LPP);
+        if (sub == 0) up = 0x00FF00FFu;           // Lp[-1] = 255
+        if (sub == LPP - 1) dn = 0x00FF00FFu;     // Lp[DPL*LPP] = 255
+        if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);   // emit the previous visit before overwriting L
+        dp_step<NR>(L, C, padm, up, dn, p1x2, p2x2, negmin);
+        minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
+        posPrev = p;
+    };
+
+    // Loads run two visits ahead of the dependent chain (three input buffers, loop unrolled by three): with ~4
+    // warps per scheduler a visit takes several hundred cycles, so two visits cover an L2 miss.
+    StepInput<NR> in0, in1, in2;
+    uint32_t q0 = pos, q1 = 0, q2 = 0;
+    int t0 = tcol, t1 = 0, t2 = 0;
+    load_step<NR>(P, pos, sub, in0);
+    if (1 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR>(P, pos, sub, in1); }
+    if (2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR>(P, pos, sub, in2); }
+    // ---- first pixel: L = C (SemiGlobalMatching.c:266-275)
+    cost(in0, t0);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
+    minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
+    gPrev = in0.g;
+    posPrev = q0;
+
+    int s = 1;      // next visit to process; its inputs are in buffer s % 3, visits s+1 and s+2 are in flight
+    while (s < len) {
+        if (s + 2 < len) { advance(); q0 = pos; t0 = tcol; load_step<NR>(P, pos, sub, in0); }
+        visit(in1, q1, t1);
+        if (++s >= len) break;
+        if (s + 2 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR>(P, pos, sub, in1); }
+        visit(in2, q2, t2);
+        if (++s >= len) break;
+        if (s + 2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR>(P, pos, sub, in2); }
+        visit(in0, q0, t0);
+        ++s;
+    }
+    if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);
+}
+
+// ------------------------------------------------------------------------------------------------ irregular paths
+// Generic walker (path_walker.h), one path per warp; results are added to the side buffer because an
+// irregular path visits pixels that a regular path also writes.
+template <int NR>
+__device__ __forceinline__ void aggregate_irregular(const AggParams& P, const WarpWork job, int lane)
+{
+    constexpr int DPL = 2 * NR;
+    constexpr unsigned FULL = 0xffffffffu;
+    const Dir dir = direction(job.dir);
+    uint32_t padm[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int i0 = DPL * lane + 2 * r;
+        padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
+    }
+    const int dbase = P.dmin + DPL * lane;
     const bool lane_stores = DPL * lane < P.Dp;
 
     PathWalker wk;
-    wk.start(P.W, P.H, dir.dx, dir.dy, job.path);
+    wk.start(P.W, P.H, dir.dx, dir.dy, job.firstPath);
     const int len = wk.length();
-
-    StepInput<NR> cur, nxt;
-    load_step<NR>(P, wk, lane, cur);
-    nxt = cur;
-
-    uint32_t L[NR];
-    uint32_t minPrev = 255, gPrev = 0;
+    uint32_t L[NR], C[NR];
+    uint32_t minx2 = 0x00FF00FFu, gPrev = 0;
     bool first = true;
 
-    for (int s = 0; s < len; ++s) {
-        if (s + 1 < len) {               // issue the next pixel's loads before this pixel's dependent chain
-            wk.advance();
-            load_step<NR>(P, wk, lane, nxt);
+    // The walk does not depend on data, so the inputs of later visits are fetched while the current one is
+    // processed: a ring of kAhead+1 input sets (these four warps run alone on their schedulers, nothing else
+    // hides their memory latency).
+    constexpr int kAhead = 3;
+    StepInput<NR> ring[kAhead + 1];
+    int posR[kAhead + 1], tcR[kAhead + 1], eR[kAhead + 1];
+    bool inR[kAhead + 1];
+    auto fetch = [&](int slot) {
+        posR[slot] = wk.pos; tcR[slot] = wk.tcol; inR[slot] = wk.inside(); eR[slot] = -1;
+        if (inR[slot]) { load_step<NR>(P, (uint32_t)wk.pos, lane, ring[slot]); eR[slot] = __ldg(P.entryOf + wk.pos); }
+    };
+    auto process = [&](int slot) {
+        if (!inR[slot]) return;                   // the reference's out-of-bounds visit: skipped (warp-uniform)
+        pack_cost<NR, true>(ring[slot], tcR[slot] - dbase + 1, C);
+        if (first) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
+            first = false;
+        } else {
+            int dg = (int)ring[slot].g - (int)gPrev;
+            dg = dg < 0 ? -dg : dg;
+            uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
+            uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
+            if (lane == 0) up = 0x00FF00FFu;
+            if (lane == 31) dn = 0x00FF00FFu;
+            dp_step<NR>(L, C, padm, up, dn, P.p1x2, P.p2x2[dg], __vneg2(minx2));
         }
-        if (cur.inside) {
-            // ---- matching cost C(p, d) = popc(cl ^ cR[p - d]), 127 where the right column would be < 0 (:170-177)
-            uint32_t c[DPL];
+        minx2 = group_min_x2<32>(lane_min_x2<NR>(L));
+        gPrev = ring[slot].g;
+        if (eR[slot] >= 0 && lane_stores) {
+            uint32_t* dst = P.side + ((size_t)eR[slot] * P.Dp + DPL * lane) / 2;
 #pragma unroll
-            for (int k = 0; k < DPL; ++k) c[k] = __popc(cur.cl ^ cur.v[DPL - 1 - k]);
-            if (cur.tcol < dmax_warp) {  // warp-uniform: only the first columns of a row need the per-disparity test
+            for (int r = 0; r < NR; ++r) atomicAdd(dst + r, L[r] & ~padm[r]);
+        }
+    };
+    int fetched = 0;                              // visits whose loads have been issued
 #pragma unroll
-                for (int k = 0; k < DPL; ++k) c[k] = (dbase + k > cur.tcol) ? 127u : c[k];
-            }
-            uint32_t C[NR];
+    for (int k = 0; k <= kAhead; ++k)
+        if (fetched < len) { if (fetched) wk.advance(); fetch(k); ++fetched; }
+    for (int s = 0; s < len; s += kAhead + 1) {
 #pragma unroll
-            for (int r = 0; r < NR; ++r) C[r] = c[2 * r] | (c[2 * r + 1] << 16);
-
-            if (first) {
-#pragma unroll
-                for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
-                first = false;
-            } else {
-                int dg = (int)cur.g - (int)gPrev;
-                dg = dg < 0 ? -dg : dg;
-                const uint32_t p2x2 = (uint32_t)s_p2[dg] * 0x00010001u;                 // min(256, max(P1, P2/(dg+1)))
-                const uint32_t negmin = ((0u - minPrev) & 0xFFFFu) * 0x00010001u;       // -minPrev in both fields
-                const uint32_t minx2 = minPrev * 0x00010001u; (void)minx2; (void)negmin;
-                uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
-                uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
-                if (lane == 0) up = 0x00FF00FFu;      // Lp[-1] = 255
-                if (lane == 31) dn = 0x00FF00FFu;     // Lp[64*NR] = 255
-                uint32_t Ln[NR];
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const uint32_t below = (r == 0) ? up : L[r - 1];
-                    const uint32_t above = (r == NR - 1) ? dn : L[r + 1];
-                    const uint32_t lm1 = __byte_perm(below, L[r], 0x5432);   // (Lp[d-1]) for both fields
-                    const uint32_t lp1 = __byte_perm(L[r], above, 0x5432);   // (Lp[d+1]) for both fields
-                    uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[r]);          // min(Lp[d-1]+P1, Lp[d])
-                    t = __viaddmin_u16x2(lp1, p1x2, t);                      // min(Lp[d+1]+P1, .)
-#ifdef SGMB_NO_WRAPPING_ADDMIN
-                    t = __vsub2(__vminu2(t, __vadd2(p2x2, minx2)), minx2);   // same value without relying on the 16-bit wrap
-#else
-                    t = __viaddmin_u16x2(t, negmin, p2x2);                   // min(. - minPrev, P2')  (>= 0, <= 255)
-#endif
-                    Ln[r] = (__vadd2(C[r], t) & 0x00FF00FFu) | padm[r];      // (uint8)(C + m - minPrev)
-                }
-#pragma unroll
-                for (int r = 0; r < NR; ++r) L[r] = Ln[r];
-            }
-            // ---- min over all disparities of the new L (:347,353)
-            uint32_t m = L[0];
-#pragma unroll
-            for (int r = 1; r < NR; ++r) m = __vminu2(m, L[r]);
-            m = min(m & 0xFFFFu, m >> 16);
-            minPrev = __reduce_min_sync(FULL, m);
-            gPrev = cur.g;
-
-            // ---- emit L_r(p, .)
-            if (!job.irregular) {
-                if (lane_stores) {
-                    uint8_t* dst = plane + (size_t)cur.pos * P.Dp + DPL * lane;
-                    if (NR == 1) {
-                        *reinterpret_cast<uint16_t*>(dst) = (uint16_t)__byte_perm(L[0], 0, 0x4420);
-                    } else if (NR == 2) {
-                        *reinterpret_cast<uint32_t*>(dst) = __byte_perm(L[0], L[1], 0x6420);
-                    } else {
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(L[0], L[1], 0x6420),
-                                                                    __byte_perm(L[NR - 2], L[NR - 1], 0x6420));
-                    }
-                }
-            } else {
-                const int e = __ldg(P.entryOf + cur.pos);
-                if (e >= 0 && lane_stores) {
-                    uint32_t* dst = P.side + ((size_t)e * P.Dp + DPL * lane) / 2;
-#pragma unroll
-                    for (int r = 0; r < NR; ++r) atomicAdd(dst + r, L[r] & ~padm[r]);
-                }
+        for (int k = 0; k <= kAhead; ++k) {
+            if (s + k < len) {
+                process(k);
+                if (fetched < len) { wk.advance(); fetch(k); ++fetched; }
             }
         }
-        cur = nxt;
     }
+}
+
+// NRH: registers per lane of the horizontal directions (32 lanes per path; latency-critical: H paths of W steps);
+// NRV/LPPV: layout of the vertical and diagonal directions; NRI: layout of irregular paths (32 lanes).
+template <int NRH, int NRV, int LPPV, int NRI>
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+sgm_aggregate_paths(const __grid_constant__ AggParams P)
+{
+    const int widx = blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
+    const WarpWork job = P.work[widx];
+    if (widx < P.nIrregularWarps) aggregate_irregular<NRI>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, true>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, false>(P, job, lane);
+    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false>(P, job, lane);
+    else                          aggregate_column_like<NRV, LPPV, true>(P, job, lane);
 }
 
 }  // namespace sgmb

@@ -17,12 +17,33 @@ constexpr int kMedianLaunches = 1;
 __device__ __forceinline__ bool pp_valid(float d) { return d != __int_as_float(0x7f800000); }
 
 // ------------------------------------------------------------------------------------------------ K4 speckles
-// Union-find with atomicMin links (labels only ever decrease, so the forest stays acyclic).
-__device__ __forceinline__ int uf_find(const int* lab, int x)
+// Connected components over the 8-neighbourhood; two valid neighbours are connected when |d_a - d_b| <= diff
+// (SemiGlobalMatching.c:620-624); components smaller than min_speckle_area become invalid (:633-638).
+//
+// Union-find on pixel indices (links always point to a smaller index, so the forest is acyclic), organised so
+// that a single huge component - the normal case for a good disparity map - costs almost nothing:
+//   init   every pixel is linked to the first pixel of its horizontal run inside its 32-pixel warp segment
+//          (one ballot), segments of one run are chained through their first pixel; so rows are merged without
+//          a single atomic;
+//   merge  only the unions that are not implied by others are executed: the vertical link below a pixel is
+//          skipped when the same two rows are already linked one column to the left, a diagonal link when the
+//          corresponding horizontal + vertical links exist; finds compress the path they walk;
+//   count  one atomicAdd per warp segment (its length) instead of one per pixel;
+//   apply  look up the size of the pixel's component.
+__device__ __forceinline__ bool pp_edge(float a, float b, float diff)
 {
-    int p = lab[x];
-    while (p != x) { x = p; p = lab[x]; }
-    return x;
+    return pp_valid(a) && pp_valid(b) && fabsf(__fsub_rn(a, b)) <= diff;
+}
+
+// Root of x with path compression (every node on the walked path is re-linked to the root found; values
+// written are ancestors read from the structure, so concurrent unions stay consistent).
+__device__ __forceinline__ int uf_find(int* lab, int x)
+{
+    int r = x, p;
+    while ((p = lab[r]) < r) r = p;
+    int cur = x;
+    while ((p = lab[cur]) > r) { lab[cur] = r; cur = p; }
+    return r;
 }
 
 __device__ __forceinline__ void uf_union(int* lab, int a, int b)
@@ -37,41 +58,57 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b)
     } while (!done);
 }
 
-__global__ void speckle_init(const float* __restrict__ disp, int* __restrict__ lab, int* __restrict__ size, int n)
+// grid (ceil(W/32), H), block 32: one warp per 32-pixel row segment.
+__global__ void __launch_bounds__(32) speckle_init(const float* __restrict__ disp, int* __restrict__ lab, int* __restrict__ size,
+                                                   int W, int H, float diff)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    lab[p] = pp_valid(disp[p]) ? p : -1;
+    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y;
+    const bool in = x < W;
+    const int p = y * W + x;
+    const float d = in ? disp[p] : __int_as_float(0x7f800000);
+    const float left = (in && x > 0) ? disp[p - 1] : __int_as_float(0x7f800000);
+    const bool valid = in && pp_valid(d);
+    const bool joined = valid && pp_edge(d, left, diff);             // connected to the pixel on its left
+    const unsigned starts = __ballot_sync(0xffffffffu, valid && !joined);
+    if (!in) return;
     size[p] = 0;
+    if (!valid) { lab[p] = -1; return; }
+    const unsigned below = starts & (0xffffffffu >> (31 - lane));    // run starts at lanes <= mine
+    const int segBase = p - lane;
+    if (below)          lab[p] = segBase + (31 - __clz(below));      // first pixel of the run inside this segment
+    else if (lane == 0) lab[p] = p - 1;                              // the run began in an earlier segment: chain to its last pixel
+    else                lab[p] = segBase;                            // ... through this segment's first pixel
 }
 
-// Two valid 8-neighbours are connected when |d_a - d_b| <= diff (SemiGlobalMatching.c:622-624).  Each pixel
-// links to its E, SW, S and SE neighbours, which covers every unordered neighbour pair once.
 __global__ void speckle_merge(const float* __restrict__ disp, int* lab, int W, int H, float diff)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int p = y * W + x;
-    const float d = disp[p];
-    if (!pp_valid(d)) return;
-    const int ox[4] = {1, -1, 0, 1}, oy[4] = {0, 1, 1, 1};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int qx = x + ox[k], qy = y + oy[k];
-        if (qx < 0 || qx >= W || qy >= H) continue;
-        const int q = qy * W + qx;
-        const float e = disp[q];
-        if (pp_valid(e) && fabsf(__fsub_rn(e, d)) <= diff) uf_union(lab, p, q);
-    }
+    if (x >= W || y + 1 >= H) return;
+    const int p = y * W + x, q = p + W;
+    const float inf = __int_as_float(0x7f800000);
+    const float c = disp[p];
+    if (!pp_valid(c)) return;
+    const float l = x > 0 ? disp[p - 1] : inf, r = x + 1 < W ? disp[p + 1] : inf;
+    const float bl = x > 0 ? disp[q - 1] : inf, b = disp[q], br = x + 1 < W ? disp[q + 1] : inf;
+    const bool eL = pp_edge(c, l, diff), eR = pp_edge(c, r, diff);
+    // vertical link, unless the path  c - l - bl - b  already exists
+    if (pp_edge(c, b, diff) && !(eL && pp_edge(l, bl, diff) && pp_edge(bl, b, diff))) uf_union(lab, p, q);
+    // diagonal links, unless  c - l - bl  /  c - r - br  exist (those vertical links are made by the neighbours)
+    if (pp_edge(c, bl, diff) && !(eL && pp_edge(l, bl, diff)) && !(pp_edge(c, b, diff) && pp_edge(b, bl, diff))) uf_union(lab, p, q - 1);
+    if (pp_edge(c, br, diff) && !(eR && pp_edge(r, br, diff)) && !(pp_edge(c, b, diff) && pp_edge(b, br, diff))) uf_union(lab, p, q + 1);
 }
 
-__global__ void speckle_count(int* lab, int* size, int n)
+// grid (ceil(W/32), H), block 32: flatten and add each warp segment's length to its root.
+__global__ void __launch_bounds__(32) speckle_count(int* lab, int* size, int W, int H)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n || lab[p] < 0) return;
-    const int r = uf_find(lab, p);
-    lab[p] = r;      // safe: r is an ancestor of p, so every chain through p still reaches the root
-    atomicAdd(&size[r], 1);
+    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y;
+    const bool in = x < W;
+    const int p = y * W + x;
+    int root = -1;
+    if (in && lab[p] >= 0) { root = uf_find(lab, p); lab[p] = root; }
+    // lanes with the same root inside the warp add once
+    const unsigned peers = __match_any_sync(0xffffffffu, root);
+    if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));
 }
 
 __global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ lab,
@@ -80,11 +117,8 @@ __global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ 
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     float d = in[p];
-    const int l = lab[p];
-    if (l >= 0) {
-        const int r = uf_find(lab, l);
-        if (size[r] < minArea) d = __int_as_float(0x7f800000);     // SemiGlobalMatching.c:633-638
-    }
+    const int r = lab[p];                                            // flattened by speckle_count
+    if (r >= 0 && size[r] < minArea) d = __int_as_float(0x7f800000);   // SemiGlobalMatching.c:633-638
     out[p] = d;
 }
 
@@ -95,10 +129,11 @@ static int launch_speckle_filter(const float* in, float* out, int32_t* scratch /
     const int n = W * H;
     int* lab = scratch;
     int* size = scratch + n;
-    speckle_init<<<(n + 255) / 256, 256, 0, st>>>(in, lab, size, n);
+    dim3 gseg((W + 31) / 32, H);
+    speckle_init<<<gseg, 32, 0, st>>>(in, lab, size, W, H, diff);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     speckle_merge<<<g, b, 0, st>>>(in, lab, W, H, diff);
-    speckle_count<<<(n + 255) / 256, 256, 0, st>>>(lab, size, n);
+    speckle_count<<<gseg, 32, 0, st>>>(lab, size, W, H);
     speckle_apply<<<(n + 255) / 256, 256, 0, st>>>(in, out, lab, size, n, minArea);
     return kSpeckleLaunches;
 }

@@ -80,12 +80,13 @@ struct SGMB_Context {
     int padF = 0;
     size_t copyStride = 0, planeStride = 0;
     // configuration-wide read-only device tables
-    PathWork* work = nullptr;
-    int nWork = 0;
+    WarpWork* work = nullptr;
+    int nIrregularWarps = 0, nRegularWarps = 0;
+    int lppV = 8;                 // lanes per path of the vertical / diagonal directions (horizontal: 32)
     int32_t* entryOf = nullptr;
     int nEntries = 0, nIrregular = 0;
-    uint16_t* p2tab = nullptr;
-    int p1c = 0;
+    uint32_t p2x2[256] = {};
+    uint32_t p1x2 = 0;
     // K3 launch shape
     int wtaTW = 128;
     size_t wtaSmem = 0;
@@ -114,8 +115,8 @@ static void free_slot_buffers(Slot& s)
 static void free_config(SGMB_Context* c)
 {
     for (auto& s : c->slots) free_slot_buffers(s);
-    cudaFree(c->work); cudaFree(c->entryOf); cudaFree(c->p2tab);
-    c->work = nullptr; c->entryOf = nullptr; c->p2tab = nullptr;
+    cudaFree(c->work); cudaFree(c->entryOf);
+    c->work = nullptr; c->entryOf = nullptr;
     c->configured = false; c->tapsAllocated = false;
 }
 
@@ -266,21 +267,36 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
     CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
 
-    // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel)
-    std::vector<PathWork> irregular, regular;
+    // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
+    //      Horizontal directions: one path per warp; the others: 32/lppV paths of one direction per warp.
+    c->lppV = (D <= 128) ? 8 : 16;
+    const int perWarpV = 32 / c->lppV;
+    std::vector<WarpWork> irregular, regular;
     std::vector<int32_t> entryOf(c->N, -1);
     int nEntries = 0;
-    auto push_dir = [&](int d, int npaths) {
-        for (int i = 0; i < npaths; ++i) regular.push_back(PathWork{i, (uint8_t)d, 0, 0});
+    // Profiling aid only (results are wrong when set): SGM_B200_DEBUG_DIRMASK keeps just the directions in the bit mask.
+    const char* dm = getenv("SGM_B200_DEBUG_DIRMASK");
+    const unsigned dirMask = dm ? (unsigned)strtoul(dm, nullptr, 0) : 0xFFu;
+    auto push_paths = [&](int d, const std::vector<int>& paths, int perWarp) {
+        if (!((dirMask >> d) & 1u)) return;
+        size_t i = 0;
+        while (i < paths.size()) {                 // consecutive path indices only, so a warp's groups are first..first+count-1
+            size_t j = i + 1;
+            while (j < paths.size() && (int)(j - i) < perWarp && paths[j] == paths[j - 1] + 1) ++j;
+            regular.push_back(WarpWork{paths[i], (uint8_t)d, (uint8_t)(j - i), 0});
+            i = j;
+        }
     };
-    // longest paths first: the horizontal directions have only H warps of W steps each
-    if (W >= H) { push_dir(0, H); push_dir(1, H); push_dir(2, W); push_dir(3, W); }
-    else        { push_dir(2, W); push_dir(3, W); push_dir(0, H); push_dir(1, H); }
+    auto all_paths = [&](int n) { std::vector<int> v(n); for (int i = 0; i < n; ++i) v[i] = i; return v; };
+    // longest paths first: the horizontal directions have only H paths of W steps each
+    if (W >= H) { push_paths(0, all_paths(H), 1); push_paths(1, all_paths(H), 1); push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); }
+    else        { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); push_paths(0, all_paths(H), 1); push_paths(1, all_paths(H), 1); }
     for (int d = 4; d < c->nDirs; ++d) {
         const Dir dir = direction(d);
+        std::vector<int> reg;
         for (int i = 0; i < W; ++i) {
-            if (path_is_regular(W, H, d, i)) { regular.push_back(PathWork{i, (uint8_t)d, 0, 0}); continue; }
-            irregular.push_back(PathWork{i, (uint8_t)d, 1, 0});
+            if (path_is_regular(W, H, d, i)) { reg.push_back(i); continue; }
+            irregular.push_back(WarpWork{i, (uint8_t)d, 1, 0});
             PathWalker wk;
             wk.start(W, H, dir.dx, dir.dy, i);
             for (int s = 0; s < H; ++s) {
@@ -288,24 +304,26 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
                 if (wk.inside() && entryOf[wk.pos] < 0) entryOf[wk.pos] = nEntries++;
             }
         }
+        push_paths(d, reg, perWarpV);
     }
-    std::vector<PathWork> work(irregular);
+    if (getenv("SGM_B200_DEBUG_NOIRR")) irregular.clear();      // profiling aid only (results are wrong when set)
+    std::vector<WarpWork> work(irregular);
     work.insert(work.end(), regular.begin(), regular.end());
-    c->nWork = (int)work.size();
+    c->nIrregularWarps = (int)irregular.size();
+    c->nRegularWarps = (int)regular.size();
     c->nEntries = nEntries;
     c->nIrregular = (int)irregular.size();
-    CU(cudaMalloc(&c->work, work.size() * sizeof(PathWork)));
-    CU(cudaMemcpy(c->work, work.data(), work.size() * sizeof(PathWork), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->work, work.size() * sizeof(WarpWork)));
+    CU(cudaMemcpy(c->work, work.data(), work.size() * sizeof(WarpWork), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->entryOf, c->N * sizeof(int32_t)));
     CU(cudaMemcpy(c->entryOf, entryOf.data(), c->N * sizeof(int32_t), cudaMemcpyHostToDevice));
 
-    // ---- penalty table: min(256, max(P1, P2_init / (delta + 1)))  (SemiGlobalMatching.c:335); candidates above
-    //      255 can never be selected, so clamping at 256 keeps the 16-bit fields from overflowing
-    uint16_t tab[256];
-    for (int dg = 0; dg < 256; ++dg) tab[dg] = (uint16_t)std::min(256, std::max((int)option->p1, (int)option->p2_init / (dg + 1)));
-    c->p1c = std::min(256, (int)option->p1);
-    CU(cudaMalloc(&c->p2tab, sizeof tab));
-    CU(cudaMemcpy(c->p2tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+    // ---- penalty table: min(256, max(P1, P2_init / (delta + 1)))  (SemiGlobalMatching.c:335) replicated into both
+    //      16-bit fields; candidates above 255 can never be selected, so clamping at 256 keeps the fields from
+    //      overflowing.  The table travels in the kernel parameters (constant bank).
+    for (int dg = 0; dg < 256; ++dg)
+        c->p2x2[dg] = (uint32_t)std::min(256, std::max((int)option->p1, (int)option->p2_init / (dg + 1))) * 0x00010001u;
+    c->p1x2 = (uint32_t)std::min(256, (int)option->p1) * 0x00010001u;
 
     // ---- per-slot device buffers
     for (auto& s : c->slots) {
@@ -367,15 +385,18 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     }
     {   // K2 aggregation
         AggParams p{};
-        p.img = dL; p.censusL = s.censusL; p.censusR4 = s.censusR4; p.copyStride = c->copyStride; p.padF = c->padF;
+        p.img = dL; p.censusL = s.censusL; p.censusR4 = s.censusR4; p.copyStride = (uint32_t)c->copyStride; p.padF = c->padF;
         p.planes = s.planes; p.planeStride = c->planeStride; p.side = reinterpret_cast<uint32_t*>(s.side);
-        p.entryOf = c->entryOf; p.p2tab = c->p2tab; p.work = c->work; p.nWork = c->nWork;
-        p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity; p.p1 = c->p1c;
-        const int blocks = (c->nWork + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
+        p.entryOf = c->entryOf; p.work = c->work; p.nIrregularWarps = c->nIrregularWarps; p.nRegularWarps = c->nRegularWarps;
+        p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity; p.p1x2 = c->p1x2;
+        memcpy(p.p2x2, c->p2x2, sizeof p.p2x2);
+        const int warps = c->nIrregularWarps + c->nRegularWarps;
+        const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
+        const int threads = kAggWarpsPerBlock * 32;
         if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
-        if (c->NR == 1)      sgm_aggregate_paths<1><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
-        else if (c->NR == 2) sgm_aggregate_paths<2><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
-        else                 sgm_aggregate_paths<4><<<blocks, kAggWarpsPerBlock * 32, 0, s.stream>>>(p);
+        if (c->NR == 1)      sgm_aggregate_paths<1, 4, 8, 1><<<blocks, threads, 0, s.stream>>>(p);
+        else if (c->NR == 2) sgm_aggregate_paths<2, 8, 8, 2><<<blocks, threads, 0, s.stream>>>(p);
+        else                 sgm_aggregate_paths<4, 8, 16, 4><<<blocks, threads, 0, s.stream>>>(p);
         if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
         ++nk;
     }
