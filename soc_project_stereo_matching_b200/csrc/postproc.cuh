@@ -11,8 +11,6 @@
 
 namespace sgmb {
 
-constexpr int kSpeckleLaunches = 4;
-constexpr int kMedianLaunches = 1;
 
 __device__ __forceinline__ bool pp_valid(float d) { return d != __int_as_float(0x7f800000); }
 
@@ -111,20 +109,11 @@ __global__ void __launch_bounds__(32) speckle_count(int* lab, int* size, int W, 
     if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));
 }
 
-__global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ lab,
-                              const int* __restrict__ size, int n, int minArea)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    float d = in[p];
-    const int r = lab[p];                                            // flattened by speckle_count
-    if (r >= 0 && size[r] < minArea) d = __int_as_float(0x7f800000);   // SemiGlobalMatching.c:633-638
-    out[p] = d;
-}
+// Returns the number of kernels launched.  The component sizes are applied by the consumer (K5a below, or
+// speckle_apply when the median is switched off).
+constexpr int kSpeckleLabelLaunches = 3;
 
-// Returns the number of kernels launched.
-static int launch_speckle_filter(const float* in, float* out, int32_t* scratch /* [2N] */, int W, int H, float diff,
-                                 int minArea, cudaStream_t st)
+static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, int W, int H, float diff, cudaStream_t st)
 {
     const int n = W * H;
     int* lab = scratch;
@@ -134,28 +123,67 @@ static int launch_speckle_filter(const float* in, float* out, int32_t* scratch /
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     speckle_merge<<<g, b, 0, st>>>(in, lab, W, H, diff);
     speckle_count<<<gseg, 32, 0, st>>>(lab, size, W, H);
-    speckle_apply<<<(n + 255) / 256, 256, 0, st>>>(in, out, lab, size, n, minArea);
-    return kSpeckleLaunches;
+    return kSpeckleLabelLaunches;
+}
+
+// SemiGlobalMatching.c:633-638: a pixel of a component smaller than minArea becomes invalid.
+__device__ __forceinline__ float speckle_filtered(const float* __restrict__ in, const int* __restrict__ lab,
+                                                  const int* __restrict__ size, int p, int minArea)
+{
+    float d = __ldg(in + p);
+    if (lab) {
+        const int r = __ldg(lab + p);                                // flattened by speckle_count
+        if (r >= 0 && __ldg(size + r) < minArea) d = __int_as_float(0x7f800000);
+    }
+    return d;
+}
+
+__global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ lab,
+                              const int* __restrict__ size, int n, int minArea)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[p] = speckle_filtered(in, lab, size, p, minArea);
 }
 
 // ------------------------------------------------------------------------------------------------ K5 in-place median
-// The reference filters in place in raster order, so out(i,j) is the median of
-//     out(i-1,j-1) out(i-1,j) out(i-1,j+1)        <- already filtered
+// The reference filters in place in raster order (SemiGlobalMatching.c:120 calls MedianFilter with in == out),
+// so for interior pixels out(i,j) is the median (5th smallest, :496-523) of
+//     out(i-1,j-1) out(i-1,j) out(i-1,j+1)        <- already filtered        "B" = {a, b, c, left}
 //     out(i,  j-1) in (i,  j) in (i,  j+1)
-//     in (i+1,j-1) in (i+1,j) in (i+1,j+1)
-// for interior pixels, while border pixels pass through.  (i,j) depends on (i,j-1) and (i-1,j+1), so all
-// pixels with the same t = 2i + j are independent: one thread per row, thread of row i handles column
-// t - 2i at step t.  Inside a warp (32 consecutive rows) the filtered value of the row above arrives by
-// __shfl_up_sync exactly when it is produced; filtered values never travel through memory, `in` is only
-// read and `out` only written.  Between warps (row 32g-1 -> row 32g) the producer's last lane publishes
-// (value, tag) as one 64-bit word per column in a global exchange row; the consumer warp refills 32 columns
-// at a time with one coalesced load, spinning until all 32 tags are current.  Producers never wait, blocks
-// are dispatched in index order and every dependency points to a lower warp index, so this cannot deadlock.
+//     in (i+1,j-1) in (i+1,j) in (i+1,j+1)        <- five unfiltered inputs  "A"
+// while border pixels pass through (:531-540).  (i,j) depends on (i,j-1) and (i-1,j+1), so all pixels with the
+// same s = 2i + j are independent and the critical path is W + 2H dependent medians long.  Everything that does
+// not depend on filtered values is therefore moved off that path:
 //
-// Median-of-9 on the critical path: the seven inputs known early are sorted (16 compare-exchanges, off the
-// dependency chain) and only their middle three can still be the answer; the two late inputs lo <= hi then
-// give median = med3(e3, max(e2, lo), min(e4, hi)).
-constexpr int kMedianWarpsPerBlock = 8;
+//   K5a median_prepare (fully parallel, fused with the speckle filter's last step): per pixel, sort the five
+//       unfiltered inputs and store them in the order the wavefront will read them: row group g = i / 32,
+//       lane = i % 32, step u = j + 2*lane, layout prep[g][u][k][lane] -> one coalesced 128-byte load per k and step.
+//       A border pixel stores its own value five times: the 5th smallest of {v,v,v,v,v} + any four values is v,
+//       so the wavefront needs no border test.
+//   K5b median_wavefront: one warp per 32 rows, ONE WARP PER CTA (each warp has an SM sub-partition to itself),
+//       thread of row i handles column s - 2*lane at step s.  With A sorted and (a,b) sorted one step earlier the
+//       median is the 5th smallest of two sorted lists, min_i max(A[5-i], B[i]):  16 min/max (3-input FMNMX3 at
+//       the end), five deep behind the arrival of c = out(i-1,j+1), which comes from the lane above by
+//       __shfl_up_sync exactly one step after it was produced.  Between warps (row 32g-1 -> row 32g) the
+//       producer's last lane publishes (tag, value) as one 64-bit word per column in a global exchange row; the
+//       consumer fetches 32 columns per coalesced load, one batch ahead of use, and re-polls only if a tag is
+//       stale.  Producers never wait, all CTAs are co-resident (<= 2048 one-warp CTAs) and every dependency
+//       points to a lower block index, so this cannot deadlock.
+constexpr int kMedianLaunches = 2;
+constexpr int kMedianTileW = 64;      // K5a: columns per block
+constexpr int kMedianBlockSteps = 8;  // K5b: steps per bulk-copy block
+constexpr int kMedianBatch = 4;       // K5b: blocks per exchange batch / super-block (32 steps)
+constexpr int kMedianRing = 8;        // K5b: blocks in the shared-memory ring (bulk copies run kMedianRing - 1 blocks ahead)
+constexpr int kMedianFrontPad = 8;    // K5b starts kMedianFrontPad steps early (feeds a, b of the first interior column)
+constexpr int kMedianStepBytes = 5 * 32 * 4;
+
+__host__ __device__ __forceinline__ int median_steps_padded(int W)
+{
+    constexpr int Q = kMedianBlockSteps * kMedianBatch;
+    return ((W + 62 + kMedianFrontPad + Q - 1) / Q) * Q;
+}
+
+static size_t median_prep_floats(int W, int H) { return (size_t)((H + 31) / 32) * median_steps_padded(W) * 5 * 32; }
 
 __device__ __forceinline__ void cswap(float& a, float& b)
 {
@@ -163,114 +191,241 @@ __device__ __forceinline__ void cswap(float& a, float& b)
     a = lo; b = hi;
 }
 
-__device__ __forceinline__ float median9_late2(float e0, float e1, float e2, float e3, float e4, float e5, float e6,
-                                               float l0, float l1)
+// grid (ceil(W / 64), ceil(H / 32)), block 256.  `filtered` (optional tap) receives the speckle-filtered map.
+__global__ void __launch_bounds__(256)
+median_prepare(const float* __restrict__ in, const int* __restrict__ lab, const int* __restrict__ size, int minArea,
+               float* __restrict__ filtered, float* __restrict__ prep, int W, int H)
 {
-    cswap(e0, e6); cswap(e2, e3); cswap(e4, e5);
-    cswap(e0, e2); cswap(e1, e4); cswap(e3, e6);
-    cswap(e0, e1); cswap(e2, e5); cswap(e3, e4);
-    cswap(e1, e2); cswap(e4, e6);
-    cswap(e2, e3); cswap(e4, e5);
-    cswap(e1, e2); cswap(e3, e4); cswap(e5, e6);
-    const float lo = fminf(l0, l1), hi = fmaxf(l0, l1);
-    const float x = fmaxf(e2, lo), y = fminf(e4, hi);
-    return fmaxf(fminf(e3, x), fminf(fmaxf(e3, x), y));
+    constexpr int TW = kMedianTileW, TS = TW + 3;        // row stride 67 = 3 (mod 32): lane l reads column s - 2l -> bank (l + s) % 32
+    __shared__ float tile[33][TS];                        // rows 32g .. 32g+32, columns j0-1 .. j0+TW
+    const int g = blockIdx.y, j0 = blockIdx.x * TW, i0 = 32 * g;
+    for (int k = threadIdx.x; k < 33 * (TW + 2); k += 256) {
+        const int r = k / (TW + 2), c = k - r * (TW + 2);
+        const int i = i0 + r, j = j0 - 1 + c;
+        float v = 0.f;
+        if (i < H && j >= 0 && j < W) {
+            v = speckle_filtered(in, lab, size, i * W + j, minArea);
+            if (filtered && r < 32 && c >= 1 && c <= TW) filtered[i * W + j] = v;
+        }
+        tile[r][c] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = i0 + lane;
+    const int SP = median_steps_padded(W);
+    float* dst = prep + ((size_t)g * SP * 5) * 32 + lane;
+    // steps whose column s - 2*lane falls into this tile for some lane: s in [j0, j0 + TW + 62)
+    for (int s = j0 + warp; s < j0 + TW + 62; s += 8) {
+        const int j = s - 2 * lane;
+        if (j < j0 || j >= j0 + TW || j >= W || i >= H) continue;
+        const int c = j - j0 + 1;
+        float a0 = tile[lane][c], a1, a2, a3, a4;
+        if (i == 0 || i == H - 1 || j == 0 || j == W - 1) {
+            a1 = a2 = a3 = a4 = a0;
+        } else {
+            a1 = tile[lane][c + 1]; a2 = tile[lane + 1][c - 1]; a3 = tile[lane + 1][c]; a4 = tile[lane + 1][c + 1];
+            cswap(a0, a1); cswap(a3, a4); cswap(a2, a4); cswap(a2, a3); cswap(a0, a3);       // 9-comparator sort of five
+            cswap(a0, a2); cswap(a1, a4); cswap(a1, a3); cswap(a1, a2);
+        }
+        float* q = dst + (size_t)(s + kMedianFrontPad) * 5 * 32;
+        q[0] = a0; q[32] = a1; q[64] = a2; q[96] = a3; q[128] = a4;
+    }
 }
 
-// Prefetch distance (in steps) of the unfiltered inputs: every lane walks its own row, so its loads are
-// uncoalesced L2 hits (~300 cycles); they are issued kMedianPF steps before first use and ride in a small
-// shift register so a miss never stalls the warp-synchronous loop.
-constexpr int kMedianPF = 6;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kMedianWarpsPerBlock * 32)
-median3_inplace_wavefront(const float* __restrict__ in, float* __restrict__ out, unsigned long long* xchg,
-                          int W, int H, unsigned epoch)
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned lo, unsigned hi)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
+
+// State carried from step to step by every lane.  Only c = out(i-1, j+1) arrives late (one shuffle after the lane
+// above produced it), so everything else is folded BEFORE it arrives: e4 <= e5 are the 4th and 5th smallest of the
+// eight values known early (the five sorted unfiltered inputs A and the sorted {a, b, left}); the median of all
+// nine is then clamp(c, e4, e5) = min(max(c, e4), e5): two dependent operations behind the shuffle.
+struct MedianLane {
+    float a, b, c, left;
+};
+
+__device__ __forceinline__ void median_fold(const float* A, float a, float b, float left, float& e4, float& e5)
+{
+    const float A1 = A[0], A2 = A[32], A3 = A[64], A4 = A[96], A5 = A[128];
+    const float p = fminf(a, b), q = fmaxf(a, b);
+    const float B1 = fminf(p, left), B3 = fmaxf(q, left), B2 = fmaxf(p, fminf(q, left));     // sorted {a, b, left}
+    // k-th smallest of two sorted lists = min over i + j = k of max(A_i, B_j)
+    e4 = fminf(fminf(A4, fmaxf(A3, B1)), fminf(fmaxf(A2, B2), fmaxf(A1, B3)));
+    e5 = fminf(fminf(A5, fmaxf(A4, B1)), fminf(fmaxf(A3, B2), fmaxf(A2, B3)));
+}
+
+// 32 steps (one exchange batch, kMedianBatch bulk-copy blocks); ringLane: the lane's view of the first of them.  PRED: some lane's column may fall outside the row.
+template <bool HAS_ABOVE, bool PRED, typename Wait, typename Refill>
+__device__ __forceinline__ void median_superblock(MedianLane& st, const float* ringLane, float batch, float* op, unsigned long long* xp,
+                                                  int jBase, int Wrow, bool publishes, unsigned tag0, int lane, Wait wait, Refill refill)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int PF = kMedianPF;
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMedianWarpsPerBlock + (threadIdx.x >> 5);     // group of 32 rows
-    const int i = 32 * g + lane;
-    if (32 * g >= H) return;
-    const bool rowOk = i < H;
-    const bool hasBelow = i + 1 < H;
-    const float* inRow = in + (size_t)(rowOk ? i : 0) * W;
-    const float* inBelow = in + (size_t)(hasBelow ? i + 1 : 0) * W;
-    float* outRow = out + (size_t)(rowOk ? i : 0) * W;
-    const bool produces = (lane == 31) && (32 * (g + 1) < H);                 // someone consumes this row
-    unsigned long long* myX = xchg + (size_t)g * W;
-    const unsigned long long* aboveX = (g > 0) ? xchg + (size_t)(g - 1) * W : nullptr;
-    const unsigned tagBase = epoch << 16;
-
-    float a = 0.f, b = 0.f, c = 0.f, left = 0.f;   // out(i-1, j-1..j+1), out(i, j-1)
-    float m[PF + 2];                               // m[k] = in(i,   j + k)
-    float n[PF + 3];                               // n[k] = in(i+1, j - 1 + k)
+    constexpr int BS = kMedianBlockSteps, NB = kMedianBatch;
 #pragma unroll
-    for (int k = 0; k < PF + 2; ++k) m[k] = 0.f;
+    for (int k = 0; k < NB; ++k) {
+        wait(k);
 #pragma unroll
-    for (int k = 0; k < PF + 3; ++k) n[k] = 0.f;
-    float batch = 0.f;           // lane k holds out(32g-1, batchBase + k)
-    int batchBase = -(1 << 30);
-
-    const int tEnd = 2 * 31 + W - 1;
-    for (int t = -(PF + 2); t <= tEnd; ++t) {
-        const int j = t - 2 * lane;
-        float o = 0.f;
-        if (rowOk && j >= 0 && j < W) {
-            if (i == 0 || i == H - 1 || j == 0 || j == W - 1) o = m[0];
-            else o = median9_late2(a, b, m[0], m[1], n[0], n[1], n[2], left, c);
-            outRow[j] = o;
-            if (produces)
-                *reinterpret_cast<volatile unsigned long long*>(myX + j) =
-                    ((unsigned long long)(tagBase | (unsigned)(j + 1)) << 32) | __float_as_uint(o);
-            left = o;
-        }
-        // filtered value of the row above for column j + 2: the lane below us just produced it
-        float up = __shfl_up_sync(FULL, o, 1);
-        if (aboveX) {                        // warp-uniform: the first lane takes it from the exchange row
-            const int need = t + 2;          // lane 0's column j + 2
-            if (need >= 0 && need < W) {
-                if (need >= batchBase + 32) {
-                    batchBase = need;
-                    const int col = batchBase + lane;
-                    const unsigned want = tagBase | (unsigned)(col + 1);
-                    unsigned long long v = 0;
-                    bool ok;
-                    do {
-                        ok = true;
-                        if (col < W) {
-                            v = *reinterpret_cast<const volatile unsigned long long*>(aboveX + col);
-                            ok = (unsigned)(v >> 32) == want;
-                        }
-                    } while (!__all_sync(FULL, ok));
-                    batch = __uint_as_float((unsigned)v);
-                }
-                const float fromAbove = __shfl_sync(FULL, batch, need - batchBase);
+        for (int e = 0; e < BS; ++e) {
+            const int off = k * BS + e;
+            float e4, e5;
+            median_fold(ringLane + (k * BS + e) * 5 * 32, st.a, st.b, st.left, e4, e5);
+            const float o = fminf(fmaxf(st.c, e4), e5);
+            if (!PRED || (unsigned)(jBase + off) < (unsigned)Wrow) {
+                op[off] = o;
+                if (publishes) st_relaxed_gpu_u64(xp + off, __float_as_uint(o), tag0 + (unsigned)off);
+            }
+            st.left = o;
+            float up = __shfl_up_sync(FULL, o, 1);       // out(i-1, j+2): the c of the next step
+            if (HAS_ABOVE) {
+                const float fromAbove = __shfl_sync(FULL, batch, off);
                 if (lane == 0) up = fromAbove;
             }
+            st.a = st.b; st.b = st.c; st.c = up;
         }
-        a = b; b = c; c = up;
-#pragma unroll
-        for (int k = 0; k < PF + 1; ++k) m[k] = m[k + 1];
-#pragma unroll
-        for (int k = 0; k < PF + 2; ++k) n[k] = n[k + 1];
-        const int jn = j + PF + 2;           // column entering both windows
-        if (rowOk && jn >= 0 && jn < W) {
-            m[PF + 1] = __ldg(inRow + jn);
-            n[PF + 2] = hasBelow ? __ldg(inBelow + jn) : 0.f;
-        }
+        __syncwarp();                                     // every lane has consumed slot k
+        refill(k);
     }
+}
+
+template <bool HAS_ABOVE>
+__device__ __forceinline__ void median_wavefront_body(const float* __restrict__ prep, float* __restrict__ out, unsigned long long* xchg,
+                                                      int W, int H, unsigned epoch, float (*ring)[kMedianBlockSteps][5][32],
+                                                      unsigned long long* mbar)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int BS = kMedianBlockSteps, NB = kMedianBatch, NR = kMedianRing;
+    static_assert(NR % NB == 0 && NR >= NB, "ring must hold whole batches");
+    constexpr unsigned kBlockBytes = BS * kMedianStepBytes;
+    const int lane = threadIdx.x;
+    const int g = blockIdx.x;
+    const int i = 32 * g + lane;
+    const int Wrow = (i < H) ? W : 0;                                         // idle rows store nothing
+    const bool publishes = (lane == 31) && (32 * (g + 1) < H);                // someone consumes this row
+    float* outRow = out + (size_t)(i < H ? i : 0) * W;
+    unsigned long long* myX = xchg + (size_t)g * W;
+    const unsigned long long* aboveX = HAS_ABOVE ? xchg + (size_t)(g - 1) * W : nullptr;
+    const unsigned tagBase = epoch << 16;
+    const int SP = median_steps_padded(W);
+    const int nBlocks = SP / BS;
+    const char* src = reinterpret_cast<const char*>(prep + ((size_t)g * SP * 5) * 32);
+
+    auto issue = [&](int blk, int slot) {                 // lane 0: bulk copy of block blk into ring slot
+        const unsigned bar = smem_u32(&mbar[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBlockBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(&ring[slot][0][0][0])), "l"(src + (size_t)blk * kBlockBytes), "r"(kBlockBytes), "r"(bar) : "memory");
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[k])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) if (k < nBlocks) issue(k, k);
+    }
+    __syncwarp();
+
+#ifdef SGM_MEDIAN_DEBUG
+    unsigned long long tStart, tFirst = 0, tEnd; long long pollCount = 0, waitCycles = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
+#endif
+    MedianLane st{0.f, 0.f, 0.f, 0.f};
+    // exchange with the group above: lane k of `batch` holds out(32g-1, base + k) for the 32 steps of a super-block;
+    // `ahead` is the next batch, fetched one super-block early and verified when it becomes current
+    unsigned long long ahead = 0;
+    const int nSuper = nBlocks / NB;
+    for (int sb = 0; sb < nSuper; ++sb) {
+        const int slot0 = (sb * NB) % NR;                // ring slots of this super-block: slot0 .. slot0 + NB - 1
+        const float* ringLane = &ring[slot0][0][0][lane];
+        const int s0 = sb * NB * BS - kMedianFrontPad;   // first step of the super-block
+        float batch = 0.f;
+        if (HAS_ABOVE) {
+            const int col = s0 + 2 + lane;               // step s needs out(32g-1, s + 2) for its successor
+            const bool inRow = col >= 0 && col < W;
+            unsigned long long v = (sb > 0) ? ahead : (inRow ? ld_relaxed_gpu_u64(aboveX + col) : 0ull);
+#ifdef SGM_MEDIAN_DEBUG
+            long long w0 = clock64();
+#endif
+            while (!__all_sync(FULL, !inRow || (unsigned)(v >> 32) == (tagBase | (unsigned)(col + 1)))) {
+                __nanosleep(200);                        // do not hammer the L2 line the producer is storing to
+                v = inRow ? ld_relaxed_gpu_u64(aboveX + col) : 0ull;
+#ifdef SGM_MEDIAN_DEBUG
+                ++pollCount;
+#endif
+            }
+#ifdef SGM_MEDIAN_DEBUG
+            if (sb >= 4) waitCycles += clock64() - w0;
+            if (sb == 3) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tFirst));
+#endif
+            batch = __uint_as_float((unsigned)v);
+            const int colNext = col + NB * BS;
+            ahead = (colNext >= 0 && colNext < W) ? ld_relaxed_gpu_u64(aboveX + colNext) : 0ull;
+        }
+        const int jBase = s0 - 2 * lane;
+        float* op = outRow + jBase;
+        unsigned long long* xp = myX + jBase;
+        const unsigned tag0 = tagBase + (unsigned)(jBase + 1);      // == tagBase | (j + 1): j + 1 < 65536
+        const unsigned parity = (unsigned)((sb * NB) / NR) & 1u;
+        auto wait = [&](int k) {
+            const unsigned bar = smem_u32(&mbar[slot0 + k]);
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            } while (!__all_sync(FULL, done != 0));
+        };
+        auto refill = [&](int k) {
+            const int nextBlk = sb * NB + k + NR;
+            if (lane == 0 && nextBlk < nBlocks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(nextBlk, slot0 + k);
+            }
+            __syncwarp();
+        };
+        // all 32 lanes are inside their rows for every step of the super-block <=> s0 >= 62 and s0 + 31 < W (and the row exists)
+        const bool interior = __all_sync(FULL, Wrow > 0) && s0 >= 62 && s0 + NB * BS <= W;
+        if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        else          median_superblock<HAS_ABOVE, true>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+    }
+#ifdef SGM_MEDIAN_DEBUG
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
+    if (lane == 0) printf("median g=%d start=%llu first4=%llu end=%llu dur_us=%.1f polls=%lld waitcyc_after4=%lld nSuper=%d\n", g, tStart % 100000000ull, tFirst % 100000000ull, tEnd % 100000000ull, (tEnd - tStart) * 1e-3, pollCount, waitCycles, nSuper);
+#endif
+}
+
+__global__ void __launch_bounds__(32)
+median_wavefront(const float* __restrict__ prep, float* __restrict__ out, unsigned long long* xchg, int W, int H, unsigned epoch)
+{
+    __shared__ __align__(128) float ring[kMedianRing][kMedianBlockSteps][5][32];
+    __shared__ __align__(8) unsigned long long mbar[kMedianRing];
+    if (blockIdx.x == 0) median_wavefront_body<false>(prep, out, xchg, W, H, epoch, ring, mbar);
+    else                 median_wavefront_body<true>(prep, out, xchg, W, H, epoch, ring, mbar);
 }
 
 // `epoch` must differ between consecutive launches on the same exchange buffer (never 0: the buffer is
 // zero-initialised), so stale tags of the previous frame are never taken for current ones.
-static int launch_median3_inplace(const float* in, float* out, unsigned long long* xchg, unsigned* epoch, int W, int H,
-                                  cudaStream_t st)
+// in: disparity map before the speckle decision; lab/size: speckle labels (or NULL: no speckle filter).
+static int launch_median3_inplace(const float* in, const int* lab, const int* size, int minArea, float* filteredTap, float* prep,
+                                  float* out, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st)
 {
     *epoch = (*epoch % 65535u) + 1u;
     const int groups = (H + 31) / 32;
-    const int blocks = (groups + kMedianWarpsPerBlock - 1) / kMedianWarpsPerBlock;
-    median3_inplace_wavefront<<<blocks, kMedianWarpsPerBlock * 32, 0, st>>>(in, out, xchg, W, H, *epoch);
+    dim3 gp((W + kMedianTileW - 1) / kMedianTileW, groups);
+    median_prepare<<<gp, 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
+    median_wavefront<<<groups, 32, 0, st>>>(prep, out, xchg, W, H, *epoch);
     return kMedianLaunches;
 }
 

@@ -64,6 +64,7 @@ struct Slot {
     float* dispFinal = nullptr;
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
     unsigned long long* xchg = nullptr;   // median wavefront exchange rows [(H+31)/32][W]
+    float* medianPrep = nullptr;      // sorted unfiltered inputs in wavefront order (postproc.cuh K5a)
     unsigned medianEpoch = 0;
     bool busy = false;
 };
@@ -107,9 +108,9 @@ static void free_slot_buffers(Slot& s)
 {
     cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
-    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg);
+    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
-    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr;
+    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr;
 }
 
 static void free_config(SGMB_Context* c)
@@ -342,6 +343,9 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         const size_t xbytes = (size_t)((H + 31) / 32) * W * sizeof(unsigned long long);
         CU(cudaMalloc(&s.xchg, xbytes));
         CU(cudaMemset(s.xchg, 0, xbytes));
+        // slots of idle (row, step) pairs are never written and must hold ordinary floats
+        CU(cudaMalloc(&s.medianPrep, median_prep_floats(W, H) * sizeof(float)));
+        CU(cudaMemset(s.medianPrep, 0, median_prep_floats(W, H) * sizeof(float)));
         s.medianEpoch = 0;
         s.busy = false;
     }
@@ -417,15 +421,21 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         ++nk;
     }
     float* cur = lrOut;
+    const int32_t* lab = nullptr;
     if (doSpeckle) {
-        float* out = s.dispSpeckle;
-        nk += launch_speckle_filter(cur, out, s.labels, W, H, 1.0f, c->opt.min_speckle_area, s.stream);
-        cur = out;
+        nk += launch_speckle_labels(cur, s.labels, W, H, 1.0f, s.stream);
+        lab = s.labels;
+        if (!doMedian) {
+            speckle_apply<<<((int)c->N + 255) / 256, 256, 0, s.stream>>>(cur, s.dispSpeckle, lab, lab + c->N, (int)c->N, c->opt.min_speckle_area);
+            ++nk;
+            cur = s.dispSpeckle;
+        }
     }
     if (doMedian) {
-        float* out = s.dispFinal;
-        nk += launch_median3_inplace(cur, out, s.xchg, &s.medianEpoch, W, H, s.stream);
-        cur = out;
+        // the component sizes are applied while the median's inputs are gathered; dispSpeckle is a tap
+        nk += launch_median3_inplace(cur, lab, lab ? lab + c->N : nullptr, c->opt.min_speckle_area, (taps && lab) ? s.dispSpeckle : nullptr,
+                                     s.medianPrep, s.dispFinal, s.xchg, &s.medianEpoch, W, H, s.stream);
+        cur = s.dispFinal;
     }
     if (dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
     CU(cudaGetLastError());
@@ -568,7 +578,10 @@ extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes
         case SGMB_STAGE_DISP_LEFT_WTA: src = taps ? s.dispLeftWta : nullptr; need = N * 4; break;
         case SGMB_STAGE_DISP_RIGHT:    src = taps ? s.dispRight : nullptr; need = N * 4; break;
         case SGMB_STAGE_DISP_LR:       src = s.dispLR; need = N * 4; break;
-        case SGMB_STAGE_DISP_SPECKLE:  src = ((c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles) ? s.dispSpeckle : s.dispLR; need = N * 4; break;
+        case SGMB_STAGE_DISP_SPECKLE:
+            if ((c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles) src = (taps || !(c->pipeline & SGMB_PIPE_MEDIAN)) ? s.dispSpeckle : nullptr;
+            else src = s.dispLR;
+            need = N * 4; break;
         case SGMB_STAGE_DISP_FINAL:    src = frame_result(c, s); need = N * 4; break;
         default:
             if (stage >= SGMB_STAGE_PATH_PLANE_0 && stage < SGMB_STAGE_PATH_PLANE_0 + c->nDirs) {
@@ -601,7 +614,7 @@ extern "C" int SGMB_KernelLaunchesPerFrame(SGMB_Context* c)
     if (!c || !c->configured) return fail(SGMB_E_STATE, "not configured");
     const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
     const bool doMedian = (c->pipeline & SGMB_PIPE_MEDIAN) != 0;
-    return 3 + (doSpeckle ? kSpeckleLaunches : 0) + (doMedian ? kMedianLaunches : 0);
+    return 3 + (doSpeckle ? kSpeckleLabelLaunches + (doMedian ? 0 : 1) : 0) + (doMedian ? kMedianLaunches : 0);
 }
 
 extern "C" double SGMB_ModelBytesPerFrame(SGMB_Context* c)
