@@ -51,6 +51,7 @@ enum {
     SGMB_STAGE_DISP_LR       = 5,  /* float  [N]     after LR check             SemiGlobalMatching.c:445-470 */
     SGMB_STAGE_DISP_SPECKLE  = 6,  /* float  [N]     after speckle removal      SemiGlobalMatching.c:585-642 (needs SGMB_PIPE_TAPS) */
     SGMB_STAGE_DISP_FINAL    = 7,  /* float  [N]     what SGM_Match returns                                   */
+    SGMB_STAGE_SPECKLE_LABELS = 8, /* int32  [2*N]   speckle filter scratch: component root per pixel (-1: invalid), then size per root */
     SGMB_STAGE_PATH_PLANE_0  = 16  /* uint8  [N*D]   +r: L_r(p,d) of direction r (order of SemiGlobalMatching.c:213-220) as written by
                                       its regular paths; pixels on an irregular path hold 0 (needs SGMB_PIPE_TAPS) */
 };

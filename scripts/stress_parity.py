@@ -11,6 +11,7 @@ from pyoracle import Oracle, options
 from soc_project_stereo_matching_b200.synth import make_pair
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+taps = not (len(sys.argv) > 2 and sys.argv[2] == "notaps")
 orc = Oracle()
 cases = []
 l, r, o, want = load_golden("cone")
@@ -19,10 +20,10 @@ for (w, h, d, tex) in [(1242, 375, 128, "noise"), (1242, 375, 128, "scene"), (64
     o = options(max_disparity=d)
     l, r, _ = make_pair(w, h, d, seed=0xB200, texture=tex)
     cases.append((f"{w}x{h}x{d}/{tex}", l, r, o, orc.match(l, r, o)))
-stages = ["aggr", "disp_left_wta", "disp_right", "disp_lr", "disp_speckle", "disp_final"]
+stages = ["aggr", "disp_left_wta", "disp_right", "disp_lr", "disp_speckle", "disp_final"] if taps else ["disp_lr", "disp_final"]
 bad = {}
 with sgm.Context(0) as ctx:
-    ctx.set_pipeline(sgm.PIPE_REFERENCE | sgm.PIPE_TAPS)
+    ctx.set_pipeline(sgm.PIPE_REFERENCE | (sgm.PIPE_TAPS if taps else 0))
     for name, l, r, o, want in cases:
         ctx.configure(l.shape[1], l.shape[0], to_sgm_option(o))
         for it in range(reps):

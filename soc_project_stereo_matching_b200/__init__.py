@@ -254,6 +254,12 @@ class Context:
         _check(lib.SGMB_GetStage(self._h, sid, out.ctypes.data, out.nbytes))
         return out
 
+    def speckle_labels(self):
+        """Debug tap: (root per pixel or -1, size per root) of the speckle filter's last run."""
+        out = np.empty((2, self.height, self.width), np.int32)
+        _check(lib.SGMB_GetStage(self._h, 8, out.ctypes.data, out.nbytes))
+        return out[0], out[1]
+
     def path_plane(self, direction: int) -> np.ndarray:
         out = np.empty((self.height, self.width, self.disp_range), np.uint8)
         _check(lib.SGMB_GetStage(self._h, STAGE_PATH_PLANE_0 + direction, out.ctypes.data, out.nbytes))

@@ -25,7 +25,7 @@ __device__ __forceinline__ bool pp_valid(float d) { return d != __int_as_float(0
 //          a single atomic;
 //   merge  only the unions that are not implied by others are executed: the vertical link below a pixel is
 //          skipped when the same two rows are already linked one column to the left, a diagonal link when the
-//          corresponding horizontal + vertical links exist; finds compress the path they walk;
+//          corresponding horizontal + vertical links exist; finds split the path they walk;
 //   count  one atomicAdd per warp segment (its length) instead of one per pixel;
 //   apply  look up the size of the pixel's component.
 __device__ __forceinline__ bool pp_edge(float a, float b, float diff)
@@ -33,27 +33,42 @@ __device__ __forceinline__ bool pp_edge(float a, float b, float diff)
     return pp_valid(a) && pp_valid(b) && fabsf(__fsub_rn(a, b)) <= diff;
 }
 
-// Root of x with path compression (every node on the walked path is re-linked to the root found; values
-// written are ancestors read from the structure, so concurrent unions stay consistent).
+// Lock-free union-find in the standard form: only ROOTS are ever linked (compare-and-swap root -> smaller node), so a
+// link that a finished union relies on is never replaced by anything but a link to one of its ancestors.
+// Root of x with path splitting: every node on the walked path is re-pointed to its grandparent.  The stores are
+// plain: the node written is a non-root (forever, links only decrease) and the value is one of its ancestors, so
+// concurrent writers can only disagree about WHICH ancestor.  Loads bypass L1 (another SM may have linked the node).
 __device__ __forceinline__ int uf_find(int* lab, int x)
 {
-    int r = x, p;
-    while ((p = lab[r]) < r) r = p;
-    int cur = x;
-    while ((p = lab[cur]) > r) { lab[cur] = r; cur = p; }
-    return r;
+    int p = __ldcg(lab + x);
+    while (p != x) {
+        const int gp = __ldcg(lab + p);
+        if (gp != p) lab[x] = gp;
+        x = p; p = gp;
+    }
+    return x;
+}
+
+// Root of x without touching the structure (used once no more unions happen: every thread then stores the ROOT of
+// its own pixel, and concurrent readers see either the old parent or the root).
+__device__ __forceinline__ int uf_root(const int* lab, int x)
+{
+    int p = __ldcg(lab + x);
+    while (p != x) { x = p; p = __ldcg(lab + x); }
+    return x;
 }
 
 __device__ __forceinline__ void uf_union(int* lab, int a, int b)
 {
-    bool done = false;
-    do {
+    for (;;) {
         a = uf_find(lab, a);
         b = uf_find(lab, b);
-        if (a < b)      { const int old = atomicMin(&lab[b], a); done = (old == b); b = old; }
-        else if (b < a) { const int old = atomicMin(&lab[a], b); done = (old == a); a = old; }
-        else done = true;
-    } while (!done);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }       // the larger root is linked below the smaller one
+        const int old = atomicCAS(lab + a, a, b);
+        if (old == a) return;
+        a = old;                                            // a had been linked meanwhile: continue from its parent
+    }
 }
 
 // grid (ceil(W/32), H), block 32: one warp per 32-pixel row segment.
@@ -103,7 +118,7 @@ __global__ void __launch_bounds__(32) speckle_count(int* lab, int* size, int W, 
     const bool in = x < W;
     const int p = y * W + x;
     int root = -1;
-    if (in && lab[p] >= 0) { root = uf_find(lab, p); lab[p] = root; }
+    if (in && lab[p] >= 0) { root = uf_root(lab, p); lab[p] = root; }
     // lanes with the same root inside the warp add once
     const unsigned peers = __match_any_sync(0xffffffffu, root);
     if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));

@@ -60,6 +60,8 @@ struct Slot {
     float* dispLeftWta = nullptr;     // taps only
     float* dispRight = nullptr;       // taps only
     float* dispLR = nullptr;
+    float* rightRow = nullptr;        // K3 scratch: right-view disparities
+    uint4* wtaRecords = nullptr;      // K3 scratch: [2][N] parked scan results
     float* dispSpeckle = nullptr;
     float* dispFinal = nullptr;
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
@@ -88,8 +90,8 @@ struct SGMB_Context {
     int nEntries = 0, nIrregular = 0;
     uint32_t p2x2[256] = {};
     uint32_t p1x2 = 0;
-    // K3 launch shape
-    int wtaTW = 128;
+    // K3 launch shape: lanes per pixel (power of two >= Dp / 16), columns per tile, dynamic shared memory
+    int wtaCPP = 8, wtaTW = 32;
     size_t wtaSmem = 0;
     // L2 flush scratch for SGMB_TimeDevice
     uint8_t* flushBuf = nullptr;
@@ -108,9 +110,9 @@ static void free_slot_buffers(Slot& s)
 {
     cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
-    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep);
+    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
-    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr;
+    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr;
 }
 
 static void free_config(SGMB_Context* c)
@@ -224,10 +226,17 @@ static int alloc_taps(SGMB_Context* c)
     return SGMB_OK;
 }
 
-static size_t wta_smem_bytes(int TW, int D, int Dp, int W)
+template <int CPP>
+static int wta_prepare(SGMB_Context* c)
 {
-    const size_t ring = (size_t)(TW + D) * (Dp + 2) * 2;
-    return ((ring + 15) & ~(size_t)15) + 2 * (size_t)W * sizeof(float);
+    c->wtaCPP = CPP;
+    c->wtaTW = WtaShape<CPP>::kTW;
+    c->wtaSmem = (size_t)(2 * c->wtaTW + c->D) * WtaShape<CPP>::kRS * sizeof(uint16_t);
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
+    return SGMB_OK;
 }
 
 extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, const SGMOption* option)
@@ -257,16 +266,16 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     const int W = c->W, H = c->H;
 
     // ---- K3 launch shape
-    const size_t smemMax = 227 * 1024;
-    c->wtaTW = 0;
-    for (int tw : {128, 64, 32}) {
-        const size_t need = wta_smem_bytes(tw, D, c->Dp, W);
-        if ((tw == 128 && need <= 110 * 1024) || (tw != 128 && need <= smemMax)) { c->wtaTW = tw; c->wtaSmem = need; break; }
+    {
+        const int chunks = c->Dp / 16;
+        int rc;
+        if (chunks <= 1)      rc = wta_prepare<1>(c);
+        else if (chunks <= 2) rc = wta_prepare<2>(c);
+        else if (chunks <= 4) rc = wta_prepare<4>(c);
+        else if (chunks <= 8) rc = wta_prepare<8>(c);
+        else                  rc = wta_prepare<16>(c);
+        if (rc) return rc;
     }
-    if (!c->wtaTW) return fail(SGMB_E_UNSUPPORTED, "image row too wide for the WTA kernel's shared memory");
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
 
     // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
     //      Horizontal directions: one path per warp; the others: 32/lppV paths of one direction per warp.
@@ -337,6 +346,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
         CU(cudaMalloc(&s.side, std::max<size_t>(1, (size_t)nEntries) * c->Dp * sizeof(uint16_t) + 64));
         CU(cudaMalloc(&s.dispLR, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.rightRow, c->N * sizeof(float)));
+        CU(cudaMalloc(&s.wtaRecords, 2 * c->N * sizeof(uint4)));
         CU(cudaMalloc(&s.dispSpeckle, c->N * sizeof(float)));
         CU(cudaMalloc(&s.dispFinal, c->N * sizeof(float)));
         CU(cudaMalloc(&s.labels, 2 * c->N * sizeof(int32_t)));
@@ -414,10 +425,25 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity;
         p.checkUnique = c->opt.is_check_unique; p.oneMinusRatio = 1 - c->opt.uniqueness_ratio;
         p.checkLR = c->opt.is_check_lr; p.lrThres = c->opt.lrcheck_thres;
-        p.ringCols = c->wtaTW + D;
-        if (c->wtaTW == 128)     sgm_reduce_wta_lr<128><<<H, 256, c->wtaSmem, s.stream>>>(p);
-        else if (c->wtaTW == 64) sgm_reduce_wta_lr<64><<<H, 128, c->wtaSmem, s.stream>>>(p);
-        else                     sgm_reduce_wta_lr<32><<<H, 64, c->wtaSmem, s.stream>>>(p);
+        p.ringCols = 2 * c->wtaTW + D;
+        p.rightRow = s.rightRow;
+        p.records = s.wtaRecords;
+#define SGM_WTA_LAUNCH(CPP)                                                                                          \
+    if (c->nDirs == 8) {                                                                                             \
+        if (taps) sgm_reduce_wta_lr<CPP, 8, true><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
+        else      sgm_reduce_wta_lr<CPP, 8, false><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
+    } else {                                                                                                         \
+        if (taps) sgm_reduce_wta_lr<CPP, 4, true><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
+        else      sgm_reduce_wta_lr<CPP, 4, false><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
+    }
+        switch (c->wtaCPP) {
+            case 1:  SGM_WTA_LAUNCH(1); break;
+            case 2:  SGM_WTA_LAUNCH(2); break;
+            case 4:  SGM_WTA_LAUNCH(4); break;
+            case 8:  SGM_WTA_LAUNCH(8); break;
+            default: SGM_WTA_LAUNCH(16); break;
+        }
+#undef SGM_WTA_LAUNCH
         ++nk;
     }
     float* cur = lrOut;
@@ -583,6 +609,7 @@ extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes
             else src = s.dispLR;
             need = N * 4; break;
         case SGMB_STAGE_DISP_FINAL:    src = frame_result(c, s); need = N * 4; break;
+        case SGMB_STAGE_SPECKLE_LABELS: src = s.labels; need = 2 * N * 4; break;
         default:
             if (stage >= SGMB_STAGE_PATH_PLANE_0 && stage < SGMB_STAGE_PATH_PLANE_0 + c->nDirs) {
                 need = N * c->D;

@@ -3,20 +3,26 @@
 //
 // Restates ComputeDisparity() (SemiGlobalMatching.c:374-443, both `inverse` modes) and LRCheck()
 // (SemiGlobalMatching.c:445-470).  S(p,d) = sum_r L_r(p,d) is exactly the reference's cost_aggr after
-// CostAggregation() (SemiGlobalMatching.c:198-221,345); it only ever exists in shared memory unless the
-// taps are enabled, in which case it is also written out in the reference layout [N][D].
+// CostAggregation() (SemiGlobalMatching.c:198-221,345); it only ever exists in shared memory unless the taps
+// are enabled, in which case it is also written out in the reference layout [N][D].
 //
-// One CTA owns one image row and streams it left to right in tiles of TW columns:
-//   sum phase : all threads load the P planes of the tile with 128-bit loads (P independent loads in
-//               flight per thread), add them as packed 16-bit fields, add the side-buffer contribution of
-//               irregular paths, and store S into a shared-memory ring of TW + D columns;
-//   WTA phase : thread t < TW scans the D costs of left pixel (c0 + t); thread TW + t scans those of a right
-//               pixel whose last contributing column (x + D - 1) has just arrived: the right view reads the
-//               ring along the diagonal S[x + d][d] (SemiGlobalMatching.c:397-399).  One thread per pixel with
-//               a sequential scan needs ~4 instructions per cost and no cross-lane reduction;
-//   epilogue  : both disparity rows sit in shared memory, so LRCheck runs in the same kernel.
-// The ring row stride (Dp + 2 halfwords, an odd number of 32-bit words) makes row-wise (left view) and
-// diagonal (right view) accesses of consecutive threads hit distinct banks.
+// The kernel streams 8 (or 4) byte planes once and is meant to run at HBM speed, so the loads of the NEXT tile
+// (128 bytes per thread, straight into the registers phase A has just consumed) are in flight during phase B.
+// One CTA owns one image row and walks it left to right in tiles of TW columns:
+//   phase A : CPP lanes share a pixel, each owning 16 consecutive disparities (one 128-bit load per plane): add
+//             the planes as packed 16-bit fields (+ the side buffer of irregular paths) and store S into a
+//             shared-memory ring of 2*TW + D columns;
+//   phase B : (after one __syncthreads) half of the CTA scans the LEFT view of the tile's columns, the other half
+//             the RIGHT view of the columns that became complete with this tile (the right view reads the ring
+//             along the diagonal S[x + d][d], SemiGlobalMatching.c:397-399).  Four lanes share a pixel; keys
+//             (cost << 16 | d) make "lowest d wins ties" and "second = min over d != best" one integer min / max
+//             each (:390-393,412-419); the four partial results are combined with xor shuffles and parked,
+//             together with the two costs next to the best one, in a 16-byte record per pixel;
+//   epilogue: every thread finishes whole pixels from the records (uniqueness, border, sub-pixel fit), then
+//             LRCheck runs over the row.
+// The ring spans 2*TW + D columns so that phase A of the next tile never overwrites a column phase B still reads:
+// one barrier per tile.  Its row stride (16*CPP + 2 halfwords, an odd number of 32-bit words) spreads row-wise
+// and diagonal accesses over the banks.
 #pragma once
 
 #include <math.h>
@@ -35,79 +41,131 @@ struct WtaParams {
     float* dispLeftWta;         // optional tap [N]
     float* dispRight;           // optional tap [N]
     float* dispOut;             // [N] left disparity after the LR check (or plain WTA when LR is off)
+    float* rightRow;            // [N] scratch: right-view disparities
+    uint4* records;             // [2][N] scratch: parked (best, second best, neighbour costs) of the left / right view
     int W, H, D, Dp, dmin;
     int checkUnique;  float oneMinusRatio;   // (1 - uniqueness_ratio), formed in float like the reference
     int checkLR;      float lrThres;
-    int ringCols;               // TW + D
+    int ringCols;               // 2 * TW + D
 };
 
 __device__ __forceinline__ float sgm_invalid() { return __int_as_float(0x7f800000); }
 
-// Scan `n` costs cost(d) = base[d * stride] (d = 0..n-1; costs with d >= n count as 65535), apply the
-// uniqueness / border tests and the sub-pixel fit.  Lowest d wins ties because (cost << 16 | d) is
-// minimised; second = second order statistic of the multiset == min over d != best (:412-419).
-template <typename Fetch>
-__device__ __forceinline__ float wta_scan(Fetch fetch, int n, int D, int dmin, int checkUnique, float oneMinusRatio)
+struct WtaPair { uint32_t kmin, ksec; };   // smallest and second smallest key; key = cost << 16 | disparity index
+
+__device__ __forceinline__ void wta_push2(WtaPair& w, uint32_t ka, uint32_t kb)
 {
-    uint32_t kmin = 0xFFFFFFFFu, second = 0xFFFFu;
-#pragma unroll 4
-    for (int d = 0; d < n; ++d) {
-        const uint32_t s = fetch(d);
-        second = min(second, max(s, kmin >> 16));
-        kmin = min(kmin, (s << 16) | (uint32_t)d);
+    const uint32_t lo = min(ka, kb), hi = max(ka, kb);
+    w.ksec = min(min(w.ksec, max(w.kmin, lo)), hi);
+    w.kmin = min(w.kmin, lo);
+}
+
+__device__ __forceinline__ void wta_push1(WtaPair& w, uint32_t k)
+{
+    w.ksec = min(w.ksec, max(w.kmin, k));
+    w.kmin = min(w.kmin, k);
+}
+
+// combine the partial results of the four lanes that share a pixel (lane ids differ in bits 0 and 1)
+__device__ __forceinline__ void wta_reduce4(WtaPair& w)
+{
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        const uint32_t k2 = __shfl_xor_sync(0xffffffffu, w.kmin, o), s2 = __shfl_xor_sync(0xffffffffu, w.ksec, o);
+        w.ksec = min(min(w.ksec, s2), max(w.kmin, k2));
+        w.kmin = min(w.kmin, k2);
     }
-    const int best = (int)(kmin & 0xFFFFu);
-    const int cmin = (int)(kmin >> 16);
+}
+
+// Uniqueness / border tests and the sub-pixel fit (SemiGlobalMatching.c:412-440) from a parked record:
+// x = smallest key, y = second smallest key, z = cost(best - 1) | cost(best + 1) << 16 (65535 where the
+// reference sees UINT16_MAX).
+__device__ __forceinline__ float wta_finish(uint4 rec, int D, int dmin, int checkUnique, float oneMinusRatio)
+{
+    const int best = (int)(rec.x & 0xFFFFu);
+    const int cmin = (int)(rec.x >> 16);
+    const int second = (int)(rec.y >> 16);
     if (cmin == 0xFFFF) return sgm_invalid();          // no candidate at all (right view, x + dmin >= W)
     if (checkUnique) {
         const float lim = __fmul_rn((float)cmin, oneMinusRatio);
         const int ilim = (int)(__float2uint_rz(lim) & 0xFFFFu);            // (uint16_t)(min * (1 - ratio))  :422
-        if ((int)second - cmin <= ilim) return sgm_invalid();
+        if (second - cmin <= ilim) return sgm_invalid();
     }
     if (best == 0 || best == D - 1) return sgm_invalid();                  // :428-431
-    const int c1 = (int)(int16_t)(uint16_t)fetch(best - 1);               // :434
-    const int c2 = (int)(int16_t)(uint16_t)((best + 1 < n) ? fetch(best + 1) : 0xFFFFu);   // :435 (65535 -> -1)
+    const int c1 = (int)(int16_t)(uint16_t)(rec.z & 0xFFFFu);             // :434
+    const int c2 = (int)(int16_t)(uint16_t)(rec.z >> 16);                 // :435 (65535 -> -1)
     int denom = (int)(int16_t)(c1 + c2 - 2 * cmin);                        // :437
     if (denom < 1) denom = 1;
     return __fadd_rn((float)(best + dmin), __fdiv_rn((float)(c1 - c2), __fmul_rn((float)denom, 2.0f)));   // :440
 }
 
-template <int TW>
-__global__ void __launch_bounds__(2 * TW)
-sgm_reduce_wta_lr(WtaParams P)
+template <int CPP>
+struct WtaShape {
+    static constexpr int kThreads = CPP == 16 ? 512 : 256;
+    static constexpr int kTW = kThreads / CPP;          // columns per tile
+    static constexpr int kRS = 16 * CPP + 2;            // ring row stride in halfwords
+};
+
+template <int CPP, int NP, bool TAPS>
+__global__ void __launch_bounds__(WtaShape<CPP>::kThreads, CPP == 16 ? 1 : 3)
+sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 {
+    constexpr int THREADS = WtaShape<CPP>::kThreads, TW = WtaShape<CPP>::kTW, RS = WtaShape<CPP>::kRS;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int W = P.W, D = P.D, Dp = P.Dp;
-    const int RS = Dp + 2;                        // ring row stride in halfwords
-    const int RB = P.ringCols;
+    const int RB = P.ringCols;                    // 2*TW + D columns
     uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);
-    float* rowL = reinterpret_cast<float*>(smem_raw + (((size_t)RB * RS * 2 + 15) & ~(size_t)15));
-    float* rowR = rowL + W;
 
     const int y = blockIdx.x;
     const size_t rowBase = (size_t)y * W;
     const int tid = threadIdx.x;
-    const int vecPerPix = Dp / 16;
-    int rightDone = 0;                            // right pixels [0, rightDone) are finished
+    float* rowL = P.dispOut + rowBase;
+    float* rowR = P.rightRow + rowBase;
+    uint4* recL = P.records + rowBase;
+    uint4* recR = P.records + (size_t)P.H * W + rowBase;
 
+    // ---- phase A mapping: (pixel of the tile, 16-disparity chunk)
+    const int pix = tid / CPP, v = tid % CPP;
+    const bool chunkOk = 16 * v < Dp;             // CPP is the power of two >= Dp / 16
+    const uint8_t* srcLane = P.planes + rowBase * Dp + 16 * v;
+    // ---- phase B mapping: first half of the CTA = left view, second half = right view; four lanes per pixel
+    constexpr int HALF = THREADS / 2, GROUPS = HALF / 4;
+    const bool rightRole = tid >= HALF;
+    const int grp = (tid % HALF) / 4, sub = tid % 4;
+    const int CH = (((D + 3) / 4) + 1) & ~1;      // disparities per lane, even
+    const int k0 = sub * CH;                      // this lane scans indices [k0, min(k0 + CH, n))
+
+    uint4 cur[NP];
+    int eCur = -1;
+    const size_t planeStride = P.planeStride;
+    auto load_tile = [&](int c0, uint4 (&q)[NP], int& e) {
+        const int c = c0 + pix;
+        e = -1;
+        if (c < W && chunkOk) {
+            const uint8_t* src = srcLane + (size_t)c * Dp;
+#pragma unroll
+            for (int r = 0; r < NP; ++r) { q[r] = __ldcs(reinterpret_cast<const uint4*>(src)); src += planeStride; }
+            if (P.hasSide) e = __ldg(P.entryOf + rowBase + c);
+        }
+    };
+
+    int rightDone = 0;                            // right pixels [0, rightDone) are finished
+    int slotTile = 0;                             // c0 % RB
+    load_tile(0, cur, eCur);
     for (int c0 = 0; c0 < W; c0 += TW) {
         const int cols = min(TW, W - c0);
-        // ------------------------------------------------------------------ sum phase
-        for (int task = tid; task < cols * vecPerPix; task += 2 * TW) {
-            const int cl = task / vecPerPix, v = task - cl * vecPerPix;
-            const size_t p = rowBase + c0 + cl;
-            const uint8_t* src = P.planes + p * Dp + 16 * v;
+        const bool lastTile = (c0 + TW >= W);
+        // ------------------------------------------------------------------ phase A
+        const int c = c0 + pix;
+        if (c < W && chunkOk) {
             uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};     // even / odd disparities as 16-bit fields
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r < P.nPlanes) {
-                    const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)r * P.planeStride));
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            for (int r = 0; r < NP; ++r) {
+                const uint32_t w[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        ev[i] += w[i] & 0x00FF00FFu;
-                        od[i] += __byte_perm(w[i], 0, 0x4341);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    ev[i] += w[i] & 0x00FF00FFu;
+                    od[i] += __byte_perm(w[i], 0, 0x4341);
                 }
             }
             uint32_t out[8];                                        // natural order: (d0,d1),(d2,d3),...
@@ -116,14 +174,11 @@ sgm_reduce_wta_lr(WtaParams P)
                 out[2 * i] = __byte_perm(ev[i], od[i], 0x5410);
                 out[2 * i + 1] = __byte_perm(ev[i], od[i], 0x7632);
             }
-            if (P.hasSide) {
-                const int e = __ldg(P.entryOf + p);
-                if (e >= 0) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)e * Dp + 16 * v);
-                    const uint4 a = __ldg(sp), b = __ldg(sp + 1);
-                    out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
-                    out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
-                }
+            if (eCur >= 0) {
+                const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)eCur * Dp + 16 * v);
+                const uint4 a = __ldg(sp), b = __ldg(sp + 1);
+                out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
+                out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
             }
             if (16 * v + 16 > D) {                                  // padding disparities never win
 #pragma unroll
@@ -133,11 +188,12 @@ sgm_reduce_wta_lr(WtaParams P)
                     if (d + 1 >= D) out[i] |= 0xFFFF0000u;
                 }
             }
-            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + (size_t)((c0 + cl) % RB) * RS + 16 * v);
+            int slot = slotTile + pix; if (slot >= RB) slot -= RB;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * RS + 16 * v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = out[i];
-            if (P.S) {
-                uint16_t* g = P.S + p * D + 16 * v;
+            if (TAPS && P.S) {
+                uint16_t* g = P.S + (rowBase + c) * D + 16 * v;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int d = 16 * v + 2 * i;
@@ -146,48 +202,97 @@ sgm_reduce_wta_lr(WtaParams P)
                 }
             }
         }
+        // the loads of the next tile fly during phase B (issued only now: the sums above must not wait on them)
+        if (!lastTile) load_tile(c0 + TW, cur, eCur);
         __syncthreads();
-        // ------------------------------------------------------------------ WTA phase
-        const bool lastTile = (c0 + TW >= W);
-        if (tid < TW) {
-            if (tid < cols) {
-                const uint16_t* base = ring + (size_t)((c0 + tid) % RB) * RS;
-                const float d = wta_scan([&](int k) { return (uint32_t)base[k]; }, D, D, P.dmin, P.checkUnique, P.oneMinusRatio);
-                rowL[c0 + tid] = d;
-                if (P.dispLeftWta) P.dispLeftWta[rowBase + c0 + tid] = d;
+        // ------------------------------------------------------------------ phase B
+        if (!rightRole) {
+            for (int g0 = 0; g0 < cols; g0 += GROUPS) {                // uniform per warp: shuffles inside
+                const int gi = g0 + grp;
+                WtaPair w{0xFFFFFFFFu, 0xFFFFFFFFu};
+                int slot = slotTile + gi; if (slot >= RB) slot -= RB;
+                const uint16_t* row = ring + slot * RS;
+                if (gi < cols) {
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(row + k0);
+                    const int n2 = max(0, min(CH, D - k0)) / 2;        // whole pairs; an odd tail is handled below
+#pragma unroll 4
+                    for (int i = 0; i < n2; ++i) {
+                        const uint32_t pr = q[i];
+                        wta_push2(w, pr * 65536u + (uint32_t)(k0 + 2 * i), (pr & 0xFFFF0000u) | (uint32_t)(k0 + 2 * i + 1));
+                    }
+                    if (k0 + 2 * n2 < min(k0 + CH, D)) wta_push1(w, (uint32_t)row[k0 + 2 * n2] * 65536u + (uint32_t)(k0 + 2 * n2));
+                }
+                wta_reduce4(w);
+                if (sub == 0 && gi < cols) {
+                    const int best = (int)(w.kmin & 0xFFFFu);
+                    const uint32_t c1 = best > 0 ? row[best - 1] : 0u, c2 = best + 1 < D ? row[best + 1] : 0xFFFFu;
+                    recL[c0 + gi] = make_uint4(w.kmin, w.ksec, c1 | (c2 << 16), 0u);
+                }
             }
         } else if (P.checkLR) {
             // right pixel x is complete once column x + dmin + D - 1 has been summed (or the row has ended)
             const int rightEnd = lastTile ? W : max(0, c0 + cols - (P.dmin + D - 1));
-            for (int x = rightDone + (tid - TW); x < rightEnd; x += TW) {
-                const int first = x + P.dmin;                       // left column of disparity index 0
-                const int n = max(0, min(D, W - first));
-                int slot = first % RB;
-                const float d = wta_scan(
-                    [&](int k) {
-                        int s = slot + k; if (s >= RB) s -= RB;
-                        return (uint32_t)ring[(size_t)s * RS + k];
-                    }, n, D, P.dmin, P.checkUnique, P.oneMinusRatio);
-                rowR[x] = d;
-                if (P.dispRight) P.dispRight[rowBase + x] = d;
+            for (int x0 = rightDone; x0 < rightEnd; x0 += GROUPS) {
+                const int x = x0 + grp;
+                const int first = x + P.dmin;                         // left column of disparity index 0
+                const int n = (x < rightEnd) ? max(0, min(D, W - first)) : 0;
+                WtaPair w{0xFFFFFFFFu, 0xFFFFFFFFu};
+                int slot0 = (first - c0) + slotTile;                  // first % RB (first lies within RB columns of c0)
+                slot0 += (slot0 < 0) ? RB : 0; slot0 += (slot0 < 0) ? RB : 0; slot0 -= (slot0 >= RB) ? RB : 0;
+                {
+                    const int kEnd = min(k0 + CH, n);
+                    int slot = slot0 + k0; if (slot >= RB) slot -= RB;
+                    const int run = min(kEnd - k0, RB - slot);         // elements before the ring wraps
+                    const uint16_t* q = ring + slot * RS + k0;
+                    int i = 0;
+#pragma unroll 4
+                    for (; i < run; ++i) wta_push1(w, (uint32_t)q[i * (RS + 1)] * 65536u + (uint32_t)(k0 + i));
+                    q -= RB * RS;
+                    for (; k0 + i < kEnd; ++i) wta_push1(w, (uint32_t)q[i * (RS + 1)] * 65536u + (uint32_t)(k0 + i));
+                }
+                wta_reduce4(w);
+                if (sub == 0 && x < rightEnd) {
+                    const int best = (int)(w.kmin & 0xFFFFu);
+                    auto cost = [&](int k) -> uint32_t {
+                        if (k < 0 || k >= n) return 0xFFFFu;
+                        int sl = slot0 + k; if (sl >= RB) sl -= RB;
+                        return ring[sl * RS + k];
+                    };
+                    recR[x] = make_uint4(w.kmin, w.ksec, cost(best - 1) | (cost(best + 1) << 16), 0u);
+                }
             }
+            rightDone = max(rightDone, rightEnd);
         }
-        if (P.checkLR) rightDone = lastTile ? W : max(rightDone, max(0, c0 + cols - (P.dmin + D - 1)));
-        __syncthreads();
+        slotTile += TW; if (slotTile >= RB) slotTile -= RB;
     }
+    // ---------------------------------------------------------------------- finish whole pixels from the records
+    __syncthreads();
+    for (int x = tid; x < W; x += THREADS) {
+        const float d = wta_finish(recL[x], D, P.dmin, P.checkUnique, P.oneMinusRatio);
+        rowL[x] = d;
+        if (TAPS && P.dispLeftWta) P.dispLeftWta[rowBase + x] = d;
+        if (P.checkLR) {
+            const float r = wta_finish(recR[x], D, P.dmin, P.checkUnique, P.oneMinusRatio);
+            rowR[x] = r;
+            if (TAPS && P.dispRight) P.dispRight[rowBase + x] = r;
+        }
+    }
+    if (!P.checkLR) return;
     // ---------------------------------------------------------------------- LR check (:445-470)
-    for (int x = tid; x < W; x += 2 * TW) {
-        float d = rowL[x];
-        if (P.checkLR && d != sgm_invalid()) {
+    __syncthreads();
+    for (int x = tid; x < W; x += THREADS) {
+        const float d = rowL[x];
+        if (d != sgm_invalid()) {
             const float shifted = __fsub_rn((float)x, d);
             const int xr = __double2int_rz(__dadd_rn((double)shifted, 0.5));
-            if (xr < 0 || xr >= W) d = sgm_invalid();
+            bool keep = true;
+            if (xr < 0 || xr >= W) keep = false;
             else {
                 const float dr = rowR[xr];
-                if (dr != sgm_invalid() && fabsf(__fsub_rn(d, dr)) > P.lrThres) d = sgm_invalid();
+                if (dr != sgm_invalid() && fabsf(__fsub_rn(d, dr)) > P.lrThres) keep = false;
             }
+            if (!keep) rowL[x] = sgm_invalid();
         }
-        P.dispOut[rowBase + x] = d;
     }
 }
 
