@@ -167,18 +167,18 @@ __device__ __forceinline__ void store_plane(uint8_t* dst, const uint32_t (&L)[NR
 }
 
 // ------------------------------------------------------------------------------------------------ horizontal paths
-// One path (image row) per warp, 2*NR disparities per lane.  Only H paths exist per direction and each is W
-// dependent steps long, so this loop is latency-critical.  It contains NO global load and is software
-// pipelined: while the dependent chain of step s runs (shuffle -> DPX min/add -> warp min), the inputs of step
-// s+1 are prepared in the same basic block.
-//  * every 32 steps the warp fetches the next 32 pixels of the row with three coalesced loads (lane j holds the
-//    grey value, the left descriptor and the one new right descriptor of step 32b+1+j; fetched one block ahead)
-//    and every step broadcasts its pixel with __shfl_sync;
+// 32/LPP paths (image rows) per warp, LPP lanes per path, 2*NR disparities per lane.  Only H paths exist per
+// direction and each is W dependent steps long, so this loop is latency-critical.  It contains NO global load and
+// is software pipelined: while the dependent chain of step s runs (shuffle -> DPX min/add -> group min), the
+// inputs of step s+1 are prepared in the same basic block.
+//  * every LPP steps the lanes of a path fetch the next LPP pixels of their row with three coalesced loads (lane j
+//    of the group holds the grey value, the left descriptor and the one new right descriptor of step LPP*b+1+j;
+//    fetched one block ahead) and every step broadcasts its pixel with a width-LPP __shfl_sync;
 //  * the right-census window cR[x-d] slides by one element per step, so it lives in registers and is shifted
-//    across lanes with one __shfl_up/down per step.
+//    across the lanes of the group with one __shfl_up/down per step.
 template <int NR, bool FWD>
 struct HorizontalState {
-    uint32_t w[2 * NR];      // w[k] = cR[x - dmin - DPL*lane - k] for the column x being prepared
+    uint32_t w[2 * NR];      // w[k] = cR[x - dmin - DPL*sub - k] for the column x being prepared
     uint32_t L[NR];
     uint32_t C[NR];          // cost of the prepared step
     uint32_t p2x2;           // penalty of the prepared step
@@ -186,25 +186,25 @@ struct HorizontalState {
     uint32_t minx2;
 };
 
-// Prepare step with column x: broadcast its pixel from lane j of the block registers, slide the window, cost.
-template <int NR, bool FWD, bool BORDER>
+// Prepare step with column x: broadcast its pixel from lane j of the group's block registers, slide the window, cost.
+template <int NR, int LPP, bool FWD, bool BORDER>
 __device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD>& st, uint32_t gBlk, uint32_t clBlk,
-                                                   uint32_t crBlk, int j, int x, int lane, int dbase)
+                                                   uint32_t crBlk, int j, int x, int sub, int dbase)
 {
     constexpr int DPL = 2 * NR;
     constexpr unsigned FULL = 0xffffffffu;
-    const uint32_t g = __shfl_sync(FULL, gBlk, j);
-    const uint32_t cl = __shfl_sync(FULL, clBlk, j);
-    const uint32_t fresh = __shfl_sync(FULL, crBlk, j);
+    const uint32_t g = __shfl_sync(FULL, gBlk, j, LPP);
+    const uint32_t cl = __shfl_sync(FULL, clBlk, j, LPP);
+    const uint32_t fresh = __shfl_sync(FULL, crBlk, j, LPP);
     if (FWD) {
-        uint32_t t = __shfl_up_sync(FULL, st.w[DPL - 1], 1);
-        if (lane == 0) t = fresh;
+        uint32_t t = __shfl_up_sync(FULL, st.w[DPL - 1], 1, LPP);
+        if (sub == 0) t = fresh;
 #pragma unroll
         for (int k = DPL - 1; k > 0; --k) st.w[k] = st.w[k - 1];
         st.w[0] = t;
     } else {
-        uint32_t t = __shfl_down_sync(FULL, st.w[0], 1);
-        if (lane == 31) t = fresh;
+        uint32_t t = __shfl_down_sync(FULL, st.w[0], 1, LPP);
+        if (sub == LPP - 1) t = fresh;
 #pragma unroll
         for (int k = 0; k < DPL - 1; ++k) st.w[k] = st.w[k + 1];
         st.w[DPL - 1] = t;
@@ -226,10 +226,10 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
 }
 
 // n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
-// prepares the following step from lane i (when `more`).
-template <int NR, bool FWD, bool BORDER>
+// prepares the following step from lane i of the group (when `more`).
+template <int NR, int LPP, bool FWD, bool BORDER>
 __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD>& st, const uint32_t (&padm)[NR], int n,
-                                                 int xnext, uint32_t gBlk, uint32_t clBlk, uint32_t crBlk, int lane, int dbase,
+                                                 int xnext, uint32_t gBlk, uint32_t clBlk, uint32_t crBlk, int sub, int dbase,
                                                  uint8_t*& out, long long outStride, bool stores)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -239,48 +239,51 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
 #pragma unroll
         for (int r = 0; r < NR; ++r) Ccur[r] = st.C[r];
         const uint32_t p2 = st.p2x2;
-        uint32_t up = __shfl_up_sync(FULL, st.L[NR - 1], 1);
-        uint32_t dn = __shfl_down_sync(FULL, st.L[0], 1);
-        if (lane == 0) up = 0x00FF00FFu;
-        if (lane == 31) dn = 0x00FF00FFu;
+        uint32_t up = __shfl_up_sync(FULL, st.L[NR - 1], 1, LPP);
+        uint32_t dn = __shfl_down_sync(FULL, st.L[0], 1, LPP);
+        if (sub == 0) up = 0x00FF00FFu;
+        if (sub == LPP - 1) dn = 0x00FF00FFu;
         dp_step<NR>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
-        st.minx2 = group_min_x2<32>(lane_min_x2<NR>(st.L));
+        st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
         if (stores) store_plane<NR>(out, st.L);
         out += outStride;
         // ---- inputs of the next step (independent of the chain above)
-        horizontal_prepare<NR, FWD, BORDER>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, lane, dbase);
+        horizontal_prepare<NR, LPP, FWD, BORDER>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase);
     }
 }
 
-template <int NR, bool FWD>
+template <int NR, int LPP, bool FWD>
 __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
-    const int W = P.W, row = job.firstPath;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int grp = lane / LPP, sub = lane % LPP;
+    const bool active = grp < (int)job.count;
+    const int W = P.W, row = job.firstPath + (active ? grp : (int)job.count - 1);   // idle groups shadow the last row
     const uint32_t rowBase = (uint32_t)row * (uint32_t)W;
     const uint32_t* cR = P.censusR4 + P.padF;                       // copy 0: cR[p], zero padding in front
     uint32_t padm[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const int i0 = DPL * lane + 2 * r;
+        const int i0 = DPL * sub + 2 * r;
         padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
     }
-    const int dbase = P.dmin + DPL * lane;
-    const int dlast = P.dmin + 32 * DPL - 1;
-    const bool stores = DPL * lane < P.Dp;
+    const int dbase = P.dmin + DPL * sub;
+    const int dlast = P.dmin + LPP * DPL - 1;
+    const bool stores = active && (DPL * sub < P.Dp);
     const long long outStride = FWD ? (long long)P.Dp : -(long long)P.Dp;
-    uint8_t* out = P.planes + (size_t)job.dir * P.planeStride + ((size_t)rowBase + (FWD ? 0 : W - 1)) * P.Dp + DPL * lane;
+    uint8_t* out = P.planes + (size_t)job.dir * P.planeStride + ((size_t)rowBase + (FWD ? 0 : W - 1)) * P.Dp + DPL * sub;
 
     auto column = [&](int s) { return FWD ? s : W - 1 - s; };
-    // block b holds steps 32*b+1 .. 32*b+32 (step 0 is set up below): lane j <-> step 32*b + 1 + j
+    // block b holds steps LPP*b+1 .. LPP*b+LPP (step 0 is set up below): lane j of the group <-> step LPP*b + 1 + j
     auto load_block = [&](int b, uint32_t& gB, uint32_t& clB, uint32_t& crB) {
-        const int s = 32 * b + 1 + lane;
+        const int s = LPP * b + 1 + sub;
         gB = 0; clB = 0; crB = 0;
         if (s < W) {
             const int x = column(s);
             gB = __ldg(P.img + rowBase + x);
             clB = __ldg(P.censusL + rowBase + x);
-            const int xin = FWD ? x - P.dmin : x - P.dmin - (32 * DPL - 1);   // element entering the window on arrival at x
+            const int xin = FWD ? x - P.dmin : x - P.dmin - (LPP * DPL - 1);   // element entering the window on arrival at x
             if (xin >= 0) crB = __ldg(cR + rowBase + xin);
         }
     };
@@ -304,33 +307,32 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
             const uint32_t c1 = (dbase + 2 * r + 1 <= x0) ? __popc(cl ^ st.w[2 * r + 1]) : 127u;
             st.L[r] = (c1 * 65536u + c0) | padm[r];
         }
-        st.minx2 = group_min_x2<32>(lane_min_x2<NR>(st.L));
+        st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
         if (stores) store_plane<NR>(out, st.L);
         out += outStride;
     }
     if (W == 1) return;
     // prepare step 1 from lane 0 of block 0; afterwards every block iteration consumes one step and prepares the next
-    horizontal_prepare<NR, FWD, true>(P, st, gA, clA, crA, 0, column(1), lane, dbase);
-    // steps 1 .. W-1: step s is consumed in block (s-1)/32 at i = (s-1)%32, where step s+1 is prepared from lane i+1
+    horizontal_prepare<NR, LPP, FWD, true>(P, st, gA, clA, crA, 0, column(1), sub, dbase);
+    // steps 1 .. W-1: step s is consumed in block (s-1)/LPP at i = (s-1)%LPP, where step s+1 is prepared from lane i+1
     // of the same block, or lane 0 of the next one.  To keep one loop body, rotate the block registers by one lane:
-    // consuming position i prepares from lane i of registers that hold steps 32*b+2 .. 32*b+33.
+    // consuming position i prepares from lane i of registers that hold steps LPP*b+2 .. LPP*b+LPP+1.
     const int nsteps = W - 1;                                        // steps still to consume
     int done = 0;
-    // registers for "prepare" lanes: lane j <-> step 32*b + 2 + j  == block registers shifted down by one lane
     auto shifted = [&](uint32_t cur, uint32_t nxt) {
-        uint32_t v = __shfl_down_sync(0xffffffffu, cur, 1);
-        const uint32_t first = __shfl_sync(0xffffffffu, nxt, 0);
-        return lane == 31 ? first : v;
+        uint32_t v = __shfl_down_sync(FULL, cur, 1, LPP);
+        const uint32_t first = __shfl_sync(FULL, nxt, 0, LPP);
+        return sub == LPP - 1 ? first : v;
     };
     for (int b = 0; done < nsteps; ++b) {
         load_block(b + 1, gB, clB, crB);                             // one block ahead
         const uint32_t gS = shifted(gA, gB), clS = shifted(clA, clB), crS = shifted(crA, crB);
-        const int n = min(32, nsteps - done);                        // consume steps done+1 .. done+n, prepare done+2 .. done+n+1
+        const int n = min(LPP, nsteps - done);                       // consume steps done+1 .. done+n, prepare done+2 .. done+n+1
         const int sPrepFirst = done + 2;
         const int xa = column(min(sPrepFirst, W - 1)), xb = column(min(sPrepFirst + n - 1, W - 1));
         const bool border = min(xa, xb) < dlast;                     // warp-uniform
-        if (border) horizontal_block<NR, FWD, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, lane, dbase, out, outStride, stores);
-        else        horizontal_block<NR, FWD, false>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, lane, dbase, out, outStride, stores);
+        if (border) horizontal_block<NR, LPP, FWD, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        else        horizontal_block<NR, LPP, FWD, false>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         done += n;
         gA = gB; clA = clB; crA = crB;
     }
@@ -512,9 +514,9 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
     }
 }
 
-// NRH: registers per lane of the horizontal directions (32 lanes per path; latency-critical: H paths of W steps);
+// NRH/LPPH: layout of the horizontal directions (latency-critical: H paths of W steps);
 // NRV/LPPV: layout of the vertical and diagonal directions; NRI: layout of irregular paths (32 lanes).
-template <int NRH, int NRV, int LPPV, int NRI>
+template <int NRH, int LPPH, int NRV, int LPPV, int NRI>
 __global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
 sgm_aggregate_paths(const __grid_constant__ AggParams P)
 {
@@ -523,8 +525,8 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
     if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
     const WarpWork job = P.work[widx];
     if (widx < P.nIrregularWarps) aggregate_irregular<NRI>(P, job, lane);
-    else if (job.dir == 0)        aggregate_horizontal<NRH, true>(P, job, lane);
-    else if (job.dir == 1)        aggregate_horizontal<NRH, false>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false>(P, job, lane);
     else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false>(P, job, lane);
     else                          aggregate_column_like<NRV, LPPV, true>(P, job, lane);
 }

@@ -85,7 +85,8 @@ struct SGMB_Context {
     // configuration-wide read-only device tables
     WarpWork* work = nullptr;
     int nIrregularWarps = 0, nRegularWarps = 0;
-    int lppV = 8;                 // lanes per path of the vertical / diagonal directions (horizontal: 32)
+    int lppV = 8;                 // lanes per path of the vertical / diagonal directions
+    int lppH = 16;                // lanes per path of the horizontal directions
     int32_t* entryOf = nullptr;
     int nEntries = 0, nIrregular = 0;
     uint32_t p2x2[256] = {};
@@ -278,9 +279,11 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     }
 
     // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
-    //      Horizontal directions: one path per warp; the others: 32/lppV paths of one direction per warp.
+    //      32/lppH rows per warp for the horizontal directions, 32/lppV paths of one direction per warp otherwise.
+    //      Horizontal jobs first (measured: any other order is 6-8 % slower); all CTAs are co-resident at C2.
     c->lppV = (D <= 128) ? 8 : 16;
-    const int perWarpV = 32 / c->lppV;
+    c->lppH = 16;
+    const int perWarpV = 32 / c->lppV, perWarpH = 32 / c->lppH;
     std::vector<WarpWork> irregular, regular;
     std::vector<int32_t> entryOf(c->N, -1);
     int nEntries = 0;
@@ -299,8 +302,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     };
     auto all_paths = [&](int n) { std::vector<int> v(n); for (int i = 0; i < n; ++i) v[i] = i; return v; };
     // longest paths first: the horizontal directions have only H paths of W steps each
-    if (W >= H) { push_paths(0, all_paths(H), 1); push_paths(1, all_paths(H), 1); push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); }
-    else        { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); push_paths(0, all_paths(H), 1); push_paths(1, all_paths(H), 1); }
+    if (W >= H) { push_paths(0, all_paths(H), perWarpH); push_paths(1, all_paths(H), perWarpH); push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); }
+    else        { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); push_paths(0, all_paths(H), perWarpH); push_paths(1, all_paths(H), perWarpH); }
     for (int d = 4; d < c->nDirs; ++d) {
         const Dir dir = direction(d);
         std::vector<int> reg;
@@ -409,9 +412,9 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
         const int threads = kAggWarpsPerBlock * 32;
         if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
-        if (c->NR == 1)      sgm_aggregate_paths<1, 4, 8, 1><<<blocks, threads, 0, s.stream>>>(p);
-        else if (c->NR == 2) sgm_aggregate_paths<2, 8, 8, 2><<<blocks, threads, 0, s.stream>>>(p);
-        else                 sgm_aggregate_paths<4, 8, 16, 4><<<blocks, threads, 0, s.stream>>>(p);
+        if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1><<<blocks, threads, 0, s.stream>>>(p);
+        else if (c->NR == 2) sgm_aggregate_paths<4, 16, 8, 8, 2><<<blocks, threads, 0, s.stream>>>(p);
+        else                 sgm_aggregate_paths<8, 16, 8, 16, 4><<<blocks, threads, 0, s.stream>>>(p);
         if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
         ++nk;
     }

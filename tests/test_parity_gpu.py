@@ -182,7 +182,7 @@ def test_hotpath_pipeline_and_batch(oracle):
         for k in range(len(pairs)):
             want = oracle.match(lefts[k], rights[k], opts)
             assert_same(f"batch[{k}] full", got[k], want["disp_final"])
-        assert c.kernel_launches_per_frame() == 3 + 4 + 1
+        assert c.kernel_launches_per_frame() == 3 + 3 + 2      # hot path + speckle labelling + median (prepare, wavefront)
 
 
 def test_multi_gpu_batch_entry_point(oracle):
