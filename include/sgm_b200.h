@@ -43,7 +43,7 @@ enum {
 
 /* Stages readable with SGMB_GetStage after a Match (element type, element count; N = W*H, D = range). */
 enum {
-    SGMB_STAGE_CENSUS_LEFT   = 0,  /* uint32 [N]     census_transform_5x5       SemiGlobalMatching.c:134-159 */
+    SGMB_STAGE_CENSUS_LEFT   = 0,  /* uint32 [N]     census_transform_5x5       SemiGlobalMatching.c:134-159 (uint64 [N] with the 9x7 window) */
     SGMB_STAGE_CENSUS_RIGHT  = 1,  /* uint32 [N]                                                             */
     SGMB_STAGE_AGGR          = 2,  /* uint16 [N*D]   S(p,d), reference layout   SemiGlobalMatching.c:198-372 (needs SGMB_PIPE_TAPS) */
     SGMB_STAGE_DISP_LEFT_WTA = 3,  /* float  [N]     left view before LR check  SemiGlobalMatching.c:374-443 (needs SGMB_PIPE_TAPS) */
@@ -69,6 +69,17 @@ void SGMB_Destroy(SGMB_Context* ctx);
 /* == SGM_Initialize on an explicit context. */
 int SGMB_Configure(SGMB_Context* ctx, uint16_t width, uint16_t height, const SGMOption* option);
 int SGMB_SetPipeline(SGMB_Context* ctx, unsigned flags);
+
+/* Census window (additive extension).  5x5 (default) is the reference's
+ * census_transform_5x5 (SemiGlobalMatching.c:134-159, uint32 descriptors) and the only mode with a reference
+ * to compare against.  9x7 (9 columns, 7 rows) builds 63-bit descriptors in 64-bit words and costs them with
+ * popcll(xor): same conventions generalised (neighbour < centre -> 1, rows outer / columns inner, first comparison
+ * in the top used bit, border of 3 rows / 4 columns = 0, stage skipped for W <= 9 or H <= 7, out-of-row cost
+ * 127).  Takes effect at the next SGMB_Configure; changing it un-configures the context.  The census stage taps
+ * then hold 8-byte descriptors.  SGMB_SetGlobalCensusWindow (or env SGM_B200_CENSUS=9x7) selects it for the
+ * context behind SGM_Initialize / SGM_Match. */
+int SGMB_SetCensusWindow(SGMB_Context* ctx, int width, int height);
+int SGMB_SetGlobalCensusWindow(int width, int height);
 
 /* == SGM_Match: host pointers, blocking; H2D + kernels + D2H. */
 int SGMB_Match(SGMB_Context* ctx, const uint8_t* img_left, const uint8_t* img_right, float* disp_left);

@@ -23,7 +23,8 @@ DIRECTIONS = [(1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1), (-1, 
 
 DEFAULTS = dict(num_paths=8, min_disparity=0, max_disparity=64, check_unique=True, uniqueness_ratio=0.99,
                 check_lr=True, lrcheck_thres=1.0, remove_speckles=True, min_speckle_area=50, p1=10,
-                p2_init=150, median=True)  # main.c:48-65
+                p2_init=150, median=True,  # main.c:48-65
+                census_w=5, census_h=5)    # 5x5 = SGM.c:134-159; 9x7 = 64-bit extension, parity unpinned
 
 
 def options(**kw) -> dict:
@@ -40,13 +41,15 @@ class _Params(C.Structure):
                 ("max_disparity", C.c_int32), ("num_paths", C.c_int32), ("p1", C.c_int32),
                 ("p2_init", C.c_int32), ("check_unique", C.c_int32), ("uniqueness_ratio", C.c_float),
                 ("check_lr", C.c_int32), ("lrcheck_thres", C.c_float), ("remove_speckles", C.c_int32),
-                ("min_speckle_area", C.c_int32), ("median", C.c_int32)]
+                ("min_speckle_area", C.c_int32), ("median", C.c_int32), ("census_w", C.c_int32),
+                ("census_h", C.c_int32)]
 
 
 class _Taps(C.Structure):
     _fields_ = [("census_left", C.c_void_p), ("census_right", C.c_void_p), ("cost", C.c_void_p),
                 ("path_cost", C.c_void_p * 8), ("aggr", C.c_void_p), ("disp_left_wta", C.c_void_p),
-                ("disp_right", C.c_void_p), ("disp_lr", C.c_void_p), ("disp_speckle", C.c_void_p)]
+                ("disp_right", C.c_void_p), ("disp_lr", C.c_void_p), ("disp_speckle", C.c_void_p),
+                ("census64_left", C.c_void_p), ("census64_right", C.c_void_p)]
 
 
 def _ptr(a):
@@ -68,7 +71,8 @@ class Oracle:
     def _params(w, h, o) -> _Params:
         return _Params(w, h, o["min_disparity"], o["max_disparity"], o["num_paths"], o["p1"], o["p2_init"],
                        int(o["check_unique"]), o["uniqueness_ratio"], int(o["check_lr"]), o["lrcheck_thres"],
-                       int(o["remove_speckles"]), o["min_speckle_area"], int(o.get("median", True)))
+                       int(o["remove_speckles"]), o["min_speckle_area"], int(o.get("median", True)),
+                       int(o.get("census_w", 5)), int(o.get("census_h", 5)))
 
     def match(self, left: np.ndarray, right: np.ndarray, opts: dict, stages: bool = True,
               per_direction: bool = False) -> dict:
@@ -86,7 +90,13 @@ class Oracle:
                        disp_speckle=np.empty((h, w), np.float32))
             if opts["check_lr"]:
                 out["disp_right"] = np.empty((h, w), np.float32)
+            if (opts.get("census_w", 5), opts.get("census_h", 5)) != (5, 5):
+                # 64-bit descriptors replace the uint32 census taps (extension, parity unpinned)
+                out["census_left"] = np.zeros((h, w), np.uint64); out["census_right"] = np.zeros((h, w), np.uint64)
+                taps.census64_left = _ptr(out["census_left"]); taps.census64_right = _ptr(out["census_right"])
             for k in ("census_left", "census_right", "cost", "aggr", "disp_left_wta", "disp_right", "disp_lr", "disp_speckle"):
+                if k.startswith("census") and out[k].dtype == np.uint64:
+                    continue
                 setattr(taps, k, _ptr(out.get(k)))
             if per_direction:
                 n = 4 if opts["num_paths"] == 4 else 8

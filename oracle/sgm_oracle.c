@@ -59,6 +59,41 @@ void sgmo_cost(const uint32_t* cl, const uint32_t* cr, int W, int H, int dmin, i
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Generalised census / cost on 64-bit descriptors.  cw = ch = 5 restates SGM.c:134-159,161-196 (same
+ * bits as sgmo_census5x5, zero-extended); cw, ch = 9, 7 is the EXTENSION (63 comparisons, centre bit 31
+ * always 0, costs 0..62) -- PARITY UNPINNED, see sgm_oracle.h.
+ * ---------------------------------------------------------------------------------------------- */
+void sgmo_census(const uint8_t* img, int W, int H, int cw, int ch, uint64_t* census)
+{
+    if (!img || !census || cw < 1 || ch < 1 || cw * ch > 64 || W <= cw || H <= ch) return;
+    const int rx = cw / 2, ry = ch / 2;
+    for (int y = ry; y < H - ry; ++y)
+        for (int x = rx; x < W - rx; ++x) {
+            const uint8_t centre = img[(size_t)y * W + x];
+            uint64_t bits = 0;
+            for (int r = -ry; r <= ry; ++r)
+                for (int c = -rx; c <= rx; ++c)
+                    bits = (bits << 1) | (uint64_t)(img[(size_t)(y + r) * W + (x + c)] < centre);
+            census[(size_t)y * W + x] = bits;
+        }
+}
+
+void sgmo_cost64(const uint64_t* cl, const uint64_t* cr, int W, int H, int dmin, int dmax, uint8_t* C)
+{
+    const int D = dmax - dmin;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            uint8_t* out = C + ((size_t)y * W + x) * D;
+            const uint64_t a = cl[(size_t)y * W + x];
+            for (int d = dmin; d < dmax; ++d) {
+                const int xr = x - d;
+                out[d - dmin] = (xr < 0 || xr >= W) ? (uint8_t)(UINT8_MAX / 2)
+                                                   : (uint8_t)__builtin_popcountll(a ^ cr[(size_t)y * W + xr]);
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Path walker (SGM.c:232-256 start positions, :281-323 moves, :359-367 row/col trackers).
  * The reference keeps uint16_t row/col trackers that are advanced AFTER the wrap handling, so after
  * a wrap the column tracker runs one ahead of the true column; that drift is part of the semantics
@@ -305,9 +340,23 @@ static int run(const sgmo_params* prm, const uint8_t* left, const uint8_t* right
     float* dr = (float*)malloc(sizeof(float) * N);
     if (!cl || !cr || !C || !S || !dl || !dr) { free(cl); free(cr); free(C); free(S); free(dl); free(dr); return -2; }
 
-    sgmo_census5x5(left, W, H, cl);                                         /* SGM.c:82-83 */
-    sgmo_census5x5(right, W, H, cr);
-    sgmo_cost(cl, cr, W, H, prm->min_disparity, prm->max_disparity, C);     /* SGM.c:89 */
+    const int cw = prm->census_w ? prm->census_w : 5, ch = prm->census_h ? prm->census_h : 5;
+    uint64_t *cl64 = NULL, *cr64 = NULL;
+    if (cw == 5 && ch == 5) {
+        sgmo_census5x5(left, W, H, cl);                                     /* SGM.c:82-83 */
+        sgmo_census5x5(right, W, H, cr);
+        sgmo_cost(cl, cr, W, H, prm->min_disparity, prm->max_disparity, C); /* SGM.c:89 */
+    } else {                                                                /* extension, parity unpinned */
+        cl64 = (uint64_t*)calloc(N, sizeof(uint64_t));
+        cr64 = (uint64_t*)calloc(N, sizeof(uint64_t));
+        if (!cl64 || !cr64 || cw * ch > 64 || !(cw & 1) || !(ch & 1)) {
+            free(cl64); free(cr64); free(cl); free(cr); free(C); free(S); free(dl); free(dr);
+            return -1;
+        }
+        sgmo_census(left, W, H, cw, ch, cl64);
+        sgmo_census(right, W, H, cw, ch, cr64);
+        sgmo_cost64(cl64, cr64, W, H, prm->min_disparity, prm->max_disparity, C);
+    }
     const int ndir = (prm->num_paths == 4) ? 4 : 8;
     for (int r = 0; r < ndir; ++r) {                                        /* SGM.c:94,213-220 */
         uint16_t* contrib = (taps && taps->path_cost[r]) ? taps->path_cost[r] : NULL;
@@ -318,6 +367,10 @@ static int run(const sgmo_params* prm, const uint8_t* left, const uint8_t* right
     if (taps) {
         if (taps->census_left)  memcpy(taps->census_left, cl, N * sizeof(uint32_t));
         if (taps->census_right) memcpy(taps->census_right, cr, N * sizeof(uint32_t));
+        for (size_t i = 0; i < N; ++i) {
+            if (taps->census64_left)  taps->census64_left[i] = cl64 ? cl64[i] : cl[i];
+            if (taps->census64_right) taps->census64_right[i] = cr64 ? cr64[i] : cr[i];
+        }
         if (taps->cost)         memcpy(taps->cost, C, V);
         if (taps->aggr)         memcpy(taps->aggr, S, V * sizeof(uint16_t));
         if (taps->disp_left_wta) memcpy(taps->disp_left_wta, dl, N * sizeof(float));
@@ -334,6 +387,7 @@ static int run(const sgmo_params* prm, const uint8_t* left, const uint8_t* right
         if (prm->median) sgmo_median3_inplace(dl, W, H);                                          /* SGM.c:120 */
     }
     if (disp_out) memcpy(disp_out, dl, N * sizeof(float));                  /* SGM.c:122 */
+    free(cl64); free(cr64);
     free(cl); free(cr); free(C); free(S); free(dl); free(dr);
     return 0;
 }

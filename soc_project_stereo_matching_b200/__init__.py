@@ -74,6 +74,8 @@ def _load() -> C.CDLL:
         "SGMB_Destroy": (None, [vp]),
         "SGMB_Configure": (i32, [vp, u16, u16, C.POINTER(SGMOption)]),
         "SGMB_SetPipeline": (i32, [vp, C.c_uint]),
+        "SGMB_SetCensusWindow": (i32, [vp, i32, i32]),
+        "SGMB_SetGlobalCensusWindow": (i32, [i32, i32]),
         "SGMB_Match": (i32, [vp, vp, vp, vp]),
         "SGMB_MatchDevice": (i32, [vp, vp, vp, vp, i32]),
         "SGMB_Synchronize": (i32, [vp]),
@@ -184,6 +186,7 @@ class Context:
         self.device, self.slots = device, slots
         self.width = self.height = self.disp_range = 0
         self.option = None
+        self.census_window = (5, 5)
 
     def close(self) -> None:
         if self._h:
@@ -204,6 +207,11 @@ class Context:
 
     def set_pipeline(self, flags: int) -> None:
         _check(lib.SGMB_SetPipeline(self._h, flags))
+
+    def set_census_window(self, width: int, height: int) -> None:
+        """5x5 (reference, uint32 descriptors) or 9x7 (64-bit extension); applies at the next configure()."""
+        _check(lib.SGMB_SetCensusWindow(self._h, width, height))
+        self.census_window = (width, height)
 
     def configure(self, width: int, height: int, option: SGMOption) -> None:
         _check(lib.SGMB_Configure(self._h, width, height, C.byref(option)))
@@ -249,6 +257,8 @@ class Context:
 
     def stage(self, name: str) -> np.ndarray:
         sid, dtype, depth = STAGES[name]
+        if name.startswith("census") and self.census_window == (9, 7):
+            dtype = np.uint64
         shape = (self.height, self.width) + ((self.disp_range,) if depth == "D" else ())
         out = np.empty(shape, dtype)
         _check(lib.SGMB_GetStage(self._h, sid, out.ctypes.data, out.nbytes))

@@ -43,10 +43,16 @@ struct WarpWork {           // one warp's job
     uint16_t pad;
 };
 
+// Census descriptors are uint32_t (5x5 window, the reference's census_transform_5x5) or 64-bit words (9x7
+// window extension); the kernels are templates over the descriptor type DT.
+typedef unsigned long long desc64_t;
+__device__ __forceinline__ uint32_t desc_popc(uint32_t x) { return (uint32_t)__popc(x); }
+__device__ __forceinline__ uint32_t desc_popc(desc64_t x) { return (uint32_t)__popcll(x); }
+
 struct AggParams {
     const uint8_t* img;         // left image [N]
-    const uint32_t* censusL;    // [N]
-    const uint32_t* censusR4;   // [4][copyStride], see census.cuh
+    const void* censusL;        // DT [N]
+    const void* censusR4;       // DT [16 / sizeof(DT)][copyStride], see census.cuh
     uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
     uint8_t* planes;            // [8][planeStride]
@@ -63,33 +69,40 @@ struct AggParams {
 constexpr int kAggWarpsPerBlock = 4;
 
 // ------------------------------------------------------------------------------------------------ shared pieces
-template <int NR>
+template <int NR, typename DT>
 struct StepInput {
-    uint32_t v[2 * NR];   // right census descriptors: v[j] = cR[q_top - (2*NR-1) + j]
-    uint32_t cl;          // left census descriptor of the pixel
+    DT v[2 * NR];         // right census descriptors: v[j] = cR[q_top - (2*NR-1) + j]
+    DT cl;                // left census descriptor of the pixel
     uint32_t g;           // grey value of the pixel
 };
 
 // Loads of one pixel visit: grey value, left descriptor and the window cR[q_top-(DPL-1) .. q_top] with
 // q_top = pos - dmin - DPL*sub, fetched from the copy that makes the window 8/16-byte aligned.
-template <int NR>
-__device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int sub, StepInput<NR>& in)
+template <int NR, typename DT>
+__device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int sub, StepInput<NR, DT>& in)
 {
     constexpr int DPL = 2 * NR;
-    constexpr int VEC = DPL < 4 ? DPL : 4;
+    constexpr int PER16 = 16 / (int)sizeof(DT);           // descriptors per 128-bit load
+    constexpr int VEC = DPL < PER16 ? DPL : PER16;        // alignment unit of the window, in descriptors
     in.g = __ldg(P.img + pos);
-    in.cl = __ldg(P.censusL + pos);
+    in.cl = __ldg(static_cast<const DT*>(P.censusL) + pos);
     const uint32_t y0 = pos - (uint32_t)(P.dmin + DPL * sub + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
     const uint32_t al = (y0 + (VEC - 1)) & ~(uint32_t)(VEC - 1);
-    const uint32_t* src = P.censusR4 + ((al - y0) * P.copyStride + al);
-    if (VEC == 2) {
+    const DT* src = static_cast<const DT*>(P.censusR4) + ((al - y0) * P.copyStride + al);
+    if constexpr (sizeof(DT) == 4 && VEC == 2) {
         const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
         in.v[0] = t.x; in.v[1] = t.y;
-    } else {
+    } else if constexpr (sizeof(DT) == 4) {
 #pragma unroll
         for (int j = 0; j < DPL / 4; ++j) {
             const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + j);
             in.v[4 * j + 0] = t.x; in.v[4 * j + 1] = t.y; in.v[4 * j + 2] = t.z; in.v[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DPL / 2; ++j) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + j);
+            in.v[2 * j + 0] = ((desc64_t)t.y << 32) | t.x; in.v[2 * j + 1] = ((desc64_t)t.w << 32) | t.z;
         }
     }
 }
@@ -97,13 +110,13 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
 // Matching cost of the lane's 2*NR disparities, packed two per register (SemiGlobalMatching.c:170-177).
 // BORDER: the pixel is so close to the left image edge that some right columns are negative -> cost 127
 // for disparity indices >= nvalid.
-template <int NR, bool BORDER>
-__device__ __forceinline__ void pack_cost(const StepInput<NR>& in, int nvalid, uint32_t (&C)[NR])
+template <int NR, bool BORDER, typename DT>
+__device__ __forceinline__ void pack_cost(const StepInput<NR, DT>& in, int nvalid, uint32_t (&C)[NR])
 {
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        uint32_t c0 = __popc(in.cl ^ in.v[2 * NR - 1 - 2 * r]);
-        uint32_t c1 = __popc(in.cl ^ in.v[2 * NR - 2 - 2 * r]);
+        uint32_t c0 = desc_popc(in.cl ^ in.v[2 * NR - 1 - 2 * r]);
+        uint32_t c1 = desc_popc(in.cl ^ in.v[2 * NR - 2 - 2 * r]);
         if (BORDER) {
             c0 = (2 * r < nvalid) ? c0 : 127u;
             c1 = (2 * r + 1 < nvalid) ? c1 : 127u;
@@ -176,9 +189,9 @@ __device__ __forceinline__ void store_plane(uint8_t* dst, const uint32_t (&L)[NR
 //    fetched one block ahead) and every step broadcasts its pixel with a width-LPP __shfl_sync;
 //  * the right-census window cR[x-d] slides by one element per step, so it lives in registers and is shifted
 //    across the lanes of the group with one __shfl_up/down per step.
-template <int NR, bool FWD>
+template <int NR, bool FWD, typename DT>
 struct HorizontalState {
-    uint32_t w[2 * NR];      // w[k] = cR[x - dmin - DPL*sub - k] for the column x being prepared
+    DT w[2 * NR];            // w[k] = cR[x - dmin - DPL*sub - k] for the column x being prepared
     uint32_t L[NR];
     uint32_t C[NR];          // cost of the prepared step
     uint32_t p2x2;           // penalty of the prepared step
@@ -187,23 +200,23 @@ struct HorizontalState {
 };
 
 // Prepare step with column x: broadcast its pixel from lane j of the group's block registers, slide the window, cost.
-template <int NR, int LPP, bool FWD, bool BORDER>
-__device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD>& st, uint32_t gBlk, uint32_t clBlk,
-                                                   uint32_t crBlk, int j, int x, int sub, int dbase)
+template <int NR, int LPP, bool FWD, bool BORDER, typename DT>
+__device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD, DT>& st, uint32_t gBlk, DT clBlk,
+                                                   DT crBlk, int j, int x, int sub, int dbase)
 {
     constexpr int DPL = 2 * NR;
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t g = __shfl_sync(FULL, gBlk, j, LPP);
-    const uint32_t cl = __shfl_sync(FULL, clBlk, j, LPP);
-    const uint32_t fresh = __shfl_sync(FULL, crBlk, j, LPP);
+    const DT cl = __shfl_sync(FULL, clBlk, j, LPP);
+    const DT fresh = __shfl_sync(FULL, crBlk, j, LPP);
     if (FWD) {
-        uint32_t t = __shfl_up_sync(FULL, st.w[DPL - 1], 1, LPP);
+        DT t = __shfl_up_sync(FULL, st.w[DPL - 1], 1, LPP);
         if (sub == 0) t = fresh;
 #pragma unroll
         for (int k = DPL - 1; k > 0; --k) st.w[k] = st.w[k - 1];
         st.w[0] = t;
     } else {
-        uint32_t t = __shfl_down_sync(FULL, st.w[0], 1, LPP);
+        DT t = __shfl_down_sync(FULL, st.w[0], 1, LPP);
         if (sub == LPP - 1) t = fresh;
 #pragma unroll
         for (int k = 0; k < DPL - 1; ++k) st.w[k] = st.w[k + 1];
@@ -211,8 +224,8 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        uint32_t c0 = __popc(cl ^ st.w[2 * r]);
-        uint32_t c1 = __popc(cl ^ st.w[2 * r + 1]);
+        uint32_t c0 = desc_popc(cl ^ st.w[2 * r]);
+        uint32_t c1 = desc_popc(cl ^ st.w[2 * r + 1]);
         if (BORDER) {                                   // right column x - d < 0  ->  cost 127 (SemiGlobalMatching.c:170-172)
             c0 = (dbase + 2 * r <= x) ? c0 : 127u;
             c1 = (dbase + 2 * r + 1 <= x) ? c1 : 127u;
@@ -227,9 +240,9 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
 
 // n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
 // prepares the following step from lane i of the group (when `more`).
-template <int NR, int LPP, bool FWD, bool BORDER>
-__device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD>& st, const uint32_t (&padm)[NR], int n,
-                                                 int xnext, uint32_t gBlk, uint32_t clBlk, uint32_t crBlk, int sub, int dbase,
+template <int NR, int LPP, bool FWD, bool BORDER, typename DT>
+__device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD, DT>& st, const uint32_t (&padm)[NR], int n,
+                                                 int xnext, uint32_t gBlk, DT clBlk, DT crBlk, int sub, int dbase,
                                                  uint8_t*& out, long long outStride, bool stores)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -248,11 +261,11 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
         if (stores) store_plane<NR>(out, st.L);
         out += outStride;
         // ---- inputs of the next step (independent of the chain above)
-        horizontal_prepare<NR, LPP, FWD, BORDER>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase);
+        horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase);
     }
 }
 
-template <int NR, int LPP, bool FWD>
+template <int NR, int LPP, bool FWD, typename DT>
 __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
@@ -261,7 +274,8 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     const bool active = grp < (int)job.count;
     const int W = P.W, row = job.firstPath + (active ? grp : (int)job.count - 1);   // idle groups shadow the last row
     const uint32_t rowBase = (uint32_t)row * (uint32_t)W;
-    const uint32_t* cR = P.censusR4 + P.padF;                       // copy 0: cR[p], zero padding in front
+    const DT* cR = static_cast<const DT*>(P.censusR4) + P.padF;     // copy 0: cR[p], zero padding in front
+    const DT* cL = static_cast<const DT*>(P.censusL);
     uint32_t padm[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -276,35 +290,36 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 
     auto column = [&](int s) { return FWD ? s : W - 1 - s; };
     // block b holds steps LPP*b+1 .. LPP*b+LPP (step 0 is set up below): lane j of the group <-> step LPP*b + 1 + j
-    auto load_block = [&](int b, uint32_t& gB, uint32_t& clB, uint32_t& crB) {
+    auto load_block = [&](int b, uint32_t& gB, DT& clB, DT& crB) {
         const int s = LPP * b + 1 + sub;
         gB = 0; clB = 0; crB = 0;
         if (s < W) {
             const int x = column(s);
             gB = __ldg(P.img + rowBase + x);
-            clB = __ldg(P.censusL + rowBase + x);
+            clB = __ldg(cL + rowBase + x);
             const int xin = FWD ? x - P.dmin : x - P.dmin - (LPP * DPL - 1);   // element entering the window on arrival at x
             if (xin >= 0) crB = __ldg(cR + rowBase + xin);
         }
     };
 
-    HorizontalState<NR, FWD> st;
-    uint32_t gA, clA, crA, gB, clB, crB;
+    HorizontalState<NR, FWD, DT> st;
+    uint32_t gA, gB;
+    DT clA, crA, clB, crB;
     load_block(0, gA, clA, crA);
     // ---- step 0: window, cost, L = C (SemiGlobalMatching.c:266-275)
     {
         const int x0 = column(0);
-        const uint32_t cl = __ldg(P.censusL + rowBase + x0);
+        const DT cl = __ldg(cL + rowBase + x0);
         st.g = __ldg(P.img + rowBase + x0);
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
             const int xr = x0 - dbase - k;
-            st.w[k] = (xr >= 0) ? __ldg(cR + rowBase + xr) : 0u;
+            st.w[k] = (xr >= 0) ? __ldg(cR + rowBase + xr) : (DT)0;
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const uint32_t c0 = (dbase + 2 * r <= x0) ? __popc(cl ^ st.w[2 * r]) : 127u;
-            const uint32_t c1 = (dbase + 2 * r + 1 <= x0) ? __popc(cl ^ st.w[2 * r + 1]) : 127u;
+            const uint32_t c0 = (dbase + 2 * r <= x0) ? desc_popc(cl ^ st.w[2 * r]) : 127u;
+            const uint32_t c1 = (dbase + 2 * r + 1 <= x0) ? desc_popc(cl ^ st.w[2 * r + 1]) : 127u;
             st.L[r] = (c1 * 65536u + c0) | padm[r];
         }
         st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
@@ -313,26 +328,27 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     }
     if (W == 1) return;
     // prepare step 1 from lane 0 of block 0; afterwards every block iteration consumes one step and prepares the next
-    horizontal_prepare<NR, LPP, FWD, true>(P, st, gA, clA, crA, 0, column(1), sub, dbase);
+    horizontal_prepare<NR, LPP, FWD, true, DT>(P, st, gA, clA, crA, 0, column(1), sub, dbase);
     // steps 1 .. W-1: step s is consumed in block (s-1)/LPP at i = (s-1)%LPP, where step s+1 is prepared from lane i+1
     // of the same block, or lane 0 of the next one.  To keep one loop body, rotate the block registers by one lane:
     // consuming position i prepares from lane i of registers that hold steps LPP*b+2 .. LPP*b+LPP+1.
     const int nsteps = W - 1;                                        // steps still to consume
     int done = 0;
-    auto shifted = [&](uint32_t cur, uint32_t nxt) {
-        uint32_t v = __shfl_down_sync(FULL, cur, 1, LPP);
-        const uint32_t first = __shfl_sync(FULL, nxt, 0, LPP);
+    auto shifted = [&](auto cur, auto nxt) {
+        const auto v = __shfl_down_sync(FULL, cur, 1, LPP);
+        const auto first = __shfl_sync(FULL, nxt, 0, LPP);
         return sub == LPP - 1 ? first : v;
     };
     for (int b = 0; done < nsteps; ++b) {
         load_block(b + 1, gB, clB, crB);                             // one block ahead
-        const uint32_t gS = shifted(gA, gB), clS = shifted(clA, clB), crS = shifted(crA, crB);
+        const uint32_t gS = shifted(gA, gB);
+        const DT clS = shifted(clA, clB), crS = shifted(crA, crB);
         const int n = min(LPP, nsteps - done);                       // consume steps done+1 .. done+n, prepare done+2 .. done+n+1
         const int sPrepFirst = done + 2;
         const int xa = column(min(sPrepFirst, W - 1)), xb = column(min(sPrepFirst + n - 1, W - 1));
         const bool border = min(xa, xb) < dlast;                     // warp-uniform
-        if (border) horizontal_block<NR, LPP, FWD, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
-        else        horizontal_block<NR, LPP, FWD, false>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        if (border) horizontal_block<NR, LPP, FWD, true, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        else        horizontal_block<NR, LPP, FWD, false, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         done += n;
         gA = gB; clA = clB; crA = crB;
     }
@@ -343,7 +359,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 // with a constant stride (plus one column wrap for diagonals); 32/LPP paths of one direction share a warp and
 // every lane owns 2*NR disparities.  The loads of visit s+1 are issued before the dependent chain of visit s
 // (two input buffers, loop unrolled by two).
-template <int NR, int LPP, bool DIAG>
+template <int NR, int LPP, bool DIAG, typename DT>
 __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const WarpWork job, int lane)
 {
     static_assert(NR == 1 || NR == 2 || NR == 4 || NR == 8, "NR");
@@ -386,12 +402,12 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
             if (tcol < 0)  { tcol += W; pos += (uint32_t)W; }
         }
     };
-    auto cost = [&](const StepInput<NR>& in, int tc) {
+    auto cost = [&](const StepInput<NR, DT>& in, int tc) {
         const bool border = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
-        if (border) pack_cost<NR, true>(in, tc - dbase + 1, C);
-        else pack_cost<NR, false>(in, 0, C);
+        if (border) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
+        else pack_cost<NR, false, DT>(in, 0, C);
     };
-    auto visit = [&](const StepInput<NR>& in, uint32_t p, int tc) {
+    auto visit = [&](const StepInput<NR, DT>& in, uint32_t p, int tc) {
         cost(in, tc);
         int dg = (int)in.g - (int)gPrev;
         dg = dg < 0 ? -dg : dg;
@@ -410,12 +426,12 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
 
     // Loads run two visits ahead of the dependent chain (three input buffers, loop unrolled by three): with ~4
     // warps per scheduler a visit takes several hundred cycles, so two visits cover an L2 miss.
-    StepInput<NR> in0, in1, in2;
+    StepInput<NR, DT> in0, in1, in2;
     uint32_t q0 = pos, q1 = 0, q2 = 0;
     int t0 = tcol, t1 = 0, t2 = 0;
-    load_step<NR>(P, pos, sub, in0);
-    if (1 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR>(P, pos, sub, in1); }
-    if (2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR>(P, pos, sub, in2); }
+    load_step<NR, DT>(P, pos, sub, in0);
+    if (1 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1); }
+    if (2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2); }
     // ---- first pixel: L = C (SemiGlobalMatching.c:266-275)
     cost(in0, t0);
 #pragma unroll
@@ -426,13 +442,13 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
 
     int s = 1;      // next visit to process; its inputs are in buffer s % 3, visits s+1 and s+2 are in flight
     while (s < len) {
-        if (s + 2 < len) { advance(); q0 = pos; t0 = tcol; load_step<NR>(P, pos, sub, in0); }
+        if (s + 2 < len) { advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0); }
         visit(in1, q1, t1);
         if (++s >= len) break;
-        if (s + 2 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR>(P, pos, sub, in1); }
+        if (s + 2 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1); }
         visit(in2, q2, t2);
         if (++s >= len) break;
-        if (s + 2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR>(P, pos, sub, in2); }
+        if (s + 2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2); }
         visit(in0, q0, t0);
         ++s;
     }
@@ -442,7 +458,7 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
 // ------------------------------------------------------------------------------------------------ irregular paths
 // Generic walker (path_walker.h), one path per warp; results are added to the side buffer because an
 // irregular path visits pixels that a regular path also writes.
-template <int NR>
+template <int NR, typename DT>
 __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
@@ -468,16 +484,16 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
     // processed: a ring of kAhead+1 input sets (these four warps run alone on their schedulers, nothing else
     // hides their memory latency).
     constexpr int kAhead = 3;
-    StepInput<NR> ring[kAhead + 1];
+    StepInput<NR, DT> ring[kAhead + 1];
     int posR[kAhead + 1], tcR[kAhead + 1], eR[kAhead + 1];
     bool inR[kAhead + 1];
     auto fetch = [&](int slot) {
         posR[slot] = wk.pos; tcR[slot] = wk.tcol; inR[slot] = wk.inside(); eR[slot] = -1;
-        if (inR[slot]) { load_step<NR>(P, (uint32_t)wk.pos, lane, ring[slot]); eR[slot] = __ldg(P.entryOf + wk.pos); }
+        if (inR[slot]) { load_step<NR, DT>(P, (uint32_t)wk.pos, lane, ring[slot]); eR[slot] = __ldg(P.entryOf + wk.pos); }
     };
     auto process = [&](int slot) {
         if (!inR[slot]) return;                   // the reference's out-of-bounds visit: skipped (warp-uniform)
-        pack_cost<NR, true>(ring[slot], tcR[slot] - dbase + 1, C);
+        pack_cost<NR, true, DT>(ring[slot], tcR[slot] - dbase + 1, C);
         if (first) {
 #pragma unroll
             for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
@@ -516,7 +532,7 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
 
 // NRH/LPPH: layout of the horizontal directions (latency-critical: H paths of W steps);
 // NRV/LPPV: layout of the vertical and diagonal directions; NRI: layout of irregular paths (32 lanes).
-template <int NRH, int LPPH, int NRV, int LPPV, int NRI>
+template <int NRH, int LPPH, int NRV, int LPPV, int NRI, typename DT>
 __global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
 sgm_aggregate_paths(const __grid_constant__ AggParams P)
 {
@@ -524,11 +540,11 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
     const int lane = threadIdx.x & 31;
     if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
     const WarpWork job = P.work[widx];
-    if (widx < P.nIrregularWarps) aggregate_irregular<NRI>(P, job, lane);
-    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true>(P, job, lane);
-    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false>(P, job, lane);
-    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false>(P, job, lane);
-    else                          aggregate_column_like<NRV, LPPV, true>(P, job, lane);
+    if (widx < P.nIrregularWarps) aggregate_irregular<NRI, DT>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT>(P, job, lane);
+    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT>(P, job, lane);
+    else                          aggregate_column_like<NRV, LPPV, true, DT>(P, job, lane);
 }
 
 }  // namespace sgmb

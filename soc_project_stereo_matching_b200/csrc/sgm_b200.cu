@@ -52,8 +52,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evAgg0 = nullptr, evAgg1 = nullptr, evDone = nullptr;
     uint8_t* img[2] = {nullptr, nullptr};
-    uint32_t* censusL = nullptr;
-    uint32_t* censusR4 = nullptr;
+    void* censusL = nullptr;          // descriptors: uint32 (5x5 census) or 64-bit (9x7 census)
+    void* censusR4 = nullptr;         // [16 / descBytes][copyStride] shifted copies (census.cuh)
     uint8_t* planes = nullptr;
     uint16_t* side = nullptr;
     uint16_t* S = nullptr;            // taps only
@@ -79,6 +79,8 @@ struct SGMB_Context {
     unsigned pipeline = SGMB_PIPE_REFERENCE;
     SGMOption opt{};
     int W = 0, H = 0, D = 0, Dp = 0, NR = 0, nDirs = 8;
+    int censusW = 5, censusH = 5;     // requested window (SGMB_SetCensusWindow); takes effect at SGMB_Configure
+    int descBytes = 4;                // descriptor size of the current configuration: 4 (5x5) or 8 (9x7)
     size_t N = 0;
     int padF = 0;
     size_t copyStride = 0, planeStride = 0;
@@ -259,6 +261,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->W = width; c->H = height; c->D = D;
     c->N = (size_t)width * height;
     c->NR = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
+    c->descBytes = (c->censusW == 9 && c->censusH == 7) ? 8 : 4;
+    const int nCopies = 16 / c->descBytes;
     c->Dp = (D + 15) & ~15;
     c->nDirs = (option->num_paths == 4) ? 4 : 8;      // the reference ignores num_paths (always 8)
     c->padF = ((option->min_disparity + 64 * c->NR + 8) + 3) & ~3;
@@ -281,7 +285,9 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
     //      32/lppH rows per warp for the horizontal directions, 32/lppV paths of one direction per warp otherwise.
     //      Horizontal jobs first (measured: any other order is 6-8 % slower); all CTAs are co-resident at C2.
-    c->lppV = (D <= 128) ? 8 : 16;
+    //      64-bit descriptors double the registers of the prefetched census windows, so that mode keeps 8
+    //      disparities per lane up to D = 128 (must match the template arguments in enqueue_frame).
+    c->lppV = (D <= 128 && !(c->descBytes == 8 && D > 64)) ? 8 : 16;
     c->lppH = 16;
     const int perWarpV = 32 / c->lppV, perWarpH = 32 / c->lppH;
     std::vector<WarpWork> irregular, regular;
@@ -341,9 +347,9 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     // ---- per-slot device buffers
     for (auto& s : c->slots) {
         CU(cudaMalloc(&s.img[0], c->N + 16)); CU(cudaMalloc(&s.img[1], c->N + 16));
-        CU(cudaMalloc(&s.censusL, c->N * sizeof(uint32_t)));
-        CU(cudaMalloc(&s.censusR4, 4 * c->copyStride * sizeof(uint32_t)));
-        CU(cudaMemset(s.censusR4, 0, 4 * c->copyStride * sizeof(uint32_t)));
+        CU(cudaMalloc(&s.censusL, c->N * (size_t)c->descBytes));
+        CU(cudaMalloc(&s.censusR4, nCopies * c->copyStride * (size_t)c->descBytes));
+        CU(cudaMemset(s.censusR4, 0, nCopies * c->copyStride * (size_t)c->descBytes));
         CU(cudaMalloc(&s.planes, (size_t)c->nDirs * c->planeStride));
         // slots on an irregular path's toroidal diagonal are never written by K2 and must read as 0 in K3
         CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
@@ -366,6 +372,21 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     if (c->pipeline & SGMB_PIPE_TAPS) if (int rc = alloc_taps(c)) return rc;
     CU(cudaDeviceSynchronize());
     c->configured = true;
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_SetCensusWindow(SGMB_Context* c, int width, int height)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if (!((width == 5 && height == 5) || (width == 9 && height == 7)))
+        return fail(SGMB_E_UNSUPPORTED, "census window %dx%d is not supported (5x5 = reference, 9x7 = 64-bit extension)", width, height);
+    if (c->configured && (width != c->censusW || height != c->censusH)) {
+        // buffers and the aggregation layout depend on the descriptor size: configure again before the next match
+        if (int rc = ensure_device(c)) return rc;
+        CU(cudaDeviceSynchronize());
+        free_config(c);
+    }
+    c->censusW = width; c->censusH = height;
     return SGMB_OK;
 }
 
@@ -398,7 +419,8 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.img[0] = dL; p.img[1] = dR; p.left = s.censusL; p.right4 = s.censusR4;
         p.copyStride = c->copyStride; p.padF = c->padF; p.W = W; p.H = H;
         dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
-        sgm_census5x5<<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
+        if (c->descBytes == 4) sgm_census<5, 5, uint32_t><<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
+        else                   sgm_census<9, 7, desc64_t><<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
         ++nk;
     }
     {   // K2 aggregation
@@ -412,9 +434,15 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
         const int threads = kAggWarpsPerBlock * 32;
         if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
-        if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1><<<blocks, threads, 0, s.stream>>>(p);
-        else if (c->NR == 2) sgm_aggregate_paths<4, 16, 8, 8, 2><<<blocks, threads, 0, s.stream>>>(p);
-        else                 sgm_aggregate_paths<8, 16, 8, 16, 4><<<blocks, threads, 0, s.stream>>>(p);
+        if (c->descBytes == 4) {
+            if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
+            else if (c->NR == 2) sgm_aggregate_paths<4, 16, 8, 8, 2, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
+            else                 sgm_aggregate_paths<8, 16, 8, 16, 4, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
+        } else {
+            if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
+            else if (c->NR == 2) sgm_aggregate_paths<4, 16, 4, 16, 2, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
+            else                 sgm_aggregate_paths<8, 16, 8, 16, 4, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
+        }
         if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
         ++nk;
     }
@@ -601,8 +629,8 @@ extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes
     const void* src = nullptr;
     size_t need = 0;
     switch (stage) {
-        case SGMB_STAGE_CENSUS_LEFT:   src = s.censusL; need = N * 4; break;
-        case SGMB_STAGE_CENSUS_RIGHT:  src = s.censusR4 + c->padF; need = N * 4; break;   // copy 0 is unshifted
+        case SGMB_STAGE_CENSUS_LEFT:   src = s.censusL; need = N * c->descBytes; break;
+        case SGMB_STAGE_CENSUS_RIGHT:  src = static_cast<const uint8_t*>(s.censusR4) + (size_t)c->padF * c->descBytes; need = N * c->descBytes; break;   // copy 0 is unshifted
         case SGMB_STAGE_AGGR:          src = taps ? s.S : nullptr; need = N * c->D * 2; break;
         case SGMB_STAGE_DISP_LEFT_WTA: src = taps ? s.dispLeftWta : nullptr; need = N * 4; break;
         case SGMB_STAGE_DISP_RIGHT:    src = taps ? s.dispRight : nullptr; need = N * 4; break;
@@ -729,6 +757,7 @@ extern "C" int SGMB_RunDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t*
 // ------------------------------------------------------------------------------------------------ reference API
 static SGMB_Context* g_ctx = nullptr;
 static int g_device = -1;
+static int g_censusW = 0, g_censusH = 0;      // 0: not set -> env SGM_B200_CENSUS ("9x7") or 5x5
 static std::mutex g_mu;
 
 extern "C" SGMB_Context* SGMB_GlobalContext(void) { return g_ctx; }
@@ -741,6 +770,15 @@ extern "C" int SGMB_SetGlobalDevice(int device)
     return SGMB_OK;
 }
 
+extern "C" int SGMB_SetGlobalCensusWindow(int width, int height)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!((width == 5 && height == 5) || (width == 9 && height == 7)))
+        return fail(SGMB_E_UNSUPPORTED, "census window %dx%d is not supported", width, height);
+    g_censusW = width; g_censusH = height;       // applied by the next SGM_Initialize / SGM_Reset
+    return SGMB_OK;
+}
+
 // replaces SemiGlobalMatching.c:37-66
 extern "C" bool SGM_Initialize(uint16_t width, uint16_t height, const SGMOption* option)
 {
@@ -750,6 +788,14 @@ extern "C" bool SGM_Initialize(uint16_t width, uint16_t height, const SGMOption*
         int dev = g_device;
         if (dev < 0) { const char* e = getenv("SGM_B200_DEVICE"); dev = e ? atoi(e) : 0; }
         if (SGMB_Create(&g_ctx, dev, 1) != SGMB_OK) { g_ctx = nullptr; return false; }
+    }
+    {
+        int cw = g_censusW, ch = g_censusH;
+        if (cw == 0) {
+            const char* e = getenv("SGM_B200_CENSUS");
+            if (!e || sscanf(e, "%dx%d", &cw, &ch) != 2) { cw = 5; ch = 5; }
+        }
+        if (SGMB_SetCensusWindow(g_ctx, cw, ch) != SGMB_OK) return false;
     }
     return SGMB_Configure(g_ctx, width, height, option) == SGMB_OK;
 }

@@ -95,3 +95,31 @@ def test_portrait_is_handled_by_the_oracle_only(oracle):
     assert out["disp_final"].shape == (20, 12)
     with pytest.raises(ValueError):
         Reference(12, 20, 8)
+
+
+def test_generalised_census_equals_5x5_and_numpy_9x7(oracle):
+    """The oracle's generalised census / 64-bit cost (the 9x7 extension, parity unpinned: no reference code exists):
+    with a 5x5 window it reproduces the pinned sgmo_census5x5 path bit for bit at every stage, and its 9x7
+    descriptors equal an independent numpy restatement of the same conventions."""
+    import ctypes as C
+    from pyoracle import options
+    from soc_project_stereo_matching_b200.synth import make_pair
+    w, h, d = 70, 26, 32
+    left, right, _ = make_pair(w, h, d, seed=5, texture="scene")
+    a = oracle.match(left, right, options(max_disparity=d))
+    g = np.zeros((h, w), np.uint64)
+    oracle.lib.sgmo_census(left.ctypes.data_as(C.c_void_p), w, h, 5, 5, g.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(g, a["census_left"].astype(np.uint64))
+    b = oracle.match(left, right, options(max_disparity=d, census_w=9, census_h=7))
+    assert b["census_left"].dtype == np.uint64
+    want = np.zeros((h, w), np.uint64)
+    L = left.astype(np.int32)
+    for r in range(-3, 4):
+        for c in range(-4, 5):
+            nb = L[3 + r:h - 3 + r, 4 + c:w - 4 + c]
+            want[3:h - 3, 4:w - 4] = (want[3:h - 3, 4:w - 4] << np.uint64(1)) | (nb < L[3:h - 3, 4:w - 4]).astype(np.uint64)
+    assert np.array_equal(b["census_left"], want)
+    # cost: popcount of the xor, 127 where the right column is outside the row
+    x, dd = 40, 9
+    assert int(b["cost"][10, x, dd]) == bin(int(b["census_left"][10, x]) ^ int(b["census_right"][10, x - dd])).count("1")
+    assert int(b["cost"][10, 3, 9]) == 127 and b["cost"].max() == 127 and np.all(b["cost"][b["cost"] != 127] <= 62)

@@ -239,3 +239,66 @@ def test_full_size_properties_c3_c5(w, h, d, paths):
     assert np.all((a[v] > 0) & (a[v] < d - 1))
     assert (np.abs(a[v] - truth[v]) <= 0.5).mean() > 0.99
     assert np.all(np.isfinite(wta[v])) and np.array_equal(a[v], wta[v])
+
+
+# ---------------------------------------------------------------------------------------------- 9x7 census extension
+# No reference code exists for a 9x7 / 64-bit census: these cases are pinned by the oracle's own
+# generalisation of SemiGlobalMatching.c:134-159 only ("parity unpinned" for the census + cost step; every later
+# stage is the pinned code operating on that cost).
+CENSUS97_CASES = [
+    (64, 48, "scene", dict(max_disparity=64)),
+    (160, 40, "scene", dict(max_disparity=128)),
+    (130, 33, "noise", dict(max_disparity=100)),
+    (72, 20, "scene", dict(max_disparity=256)),
+    (300, 24, "scene", dict(max_disparity=200, min_disparity=7)),
+    (21, 40, "scene", dict(max_disparity=16)),                  # portrait
+    (50, 30, "scene", dict(max_disparity=32, num_paths=4)),
+    (9, 12, "noise", dict(max_disparity=4)),                    # census skipped entirely (W <= 9)
+    (12, 7, "noise", dict(max_disparity=4)),                    # census skipped entirely (H <= 7)
+    (10, 8, "noise", dict(max_disparity=4)),                    # one interior pixel
+    (40, 30, "noise", dict(max_disparity=1, check_unique=False)),
+]
+
+
+@pytest.mark.parametrize("w,h,tex,kw", CENSUS97_CASES)
+def test_census_9x7_against_oracle(oracle, w, h, tex, kw):
+    opts = options(census_w=9, census_h=7, **kw)
+    d = opts["max_disparity"] - opts["min_disparity"]
+    left, right, _ = make_pair(w, h, d, seed=0x97 + 31 * w + h, texture=tex)
+    want = oracle.match(left, right, opts)
+    with sgm.Context(0) as c:
+        c.set_pipeline(sgm.PIPE_REFERENCE | sgm.PIPE_TAPS)
+        c.set_census_window(9, 7)
+        got = run_all_stages(c, left, right, opts)
+        assert got["census_left"].dtype == np.uint64
+        compare_stages(f"9x7:{w}x{h}x{d}", got, want)
+        # switching back to the reference's window on the same context gives the 5x5 result again
+        c.set_census_window(5, 5)
+        opts5 = options(**kw)
+        compare_stages(f"5x5 after 9x7:{w}x{h}x{d}", run_all_stages(c, left, right, opts5), oracle.match(left, right, opts5))
+
+
+def test_census_9x7_kitti_shape_and_global_api(oracle):
+    """C2 shape with the 9x7 window through SGM_Initialize/SGM_Match (SGMB_SetGlobalCensusWindow) and a context."""
+    w, h, d = 1242, 375, 128
+    opts = options(max_disparity=d, census_w=9, census_h=7)
+    left, right, truth = make_pair(w, h, d, seed=0xB200, texture="scene")
+    want = oracle.match(left, right, opts, stages=True)
+    try:
+        assert sgm.lib.SGMB_SetGlobalCensusWindow(9, 7) == 0
+        assert sgm.SGM_Initialize(w, h, to_sgm_option(opts))
+        out = np.zeros((h, w), np.float32)
+        assert sgm.SGM_Match(left, right, out)
+        assert_same("9x7 SGM_Match", out, want["disp_final"])
+    finally:
+        assert sgm.lib.SGMB_SetGlobalCensusWindow(5, 5) == 0
+    assert sgm.lib.SGMB_SetGlobalCensusWindow(7, 7) != 0                 # unsupported window
+    with sgm.Context(0) as c:
+        c.set_pipeline(sgm.PIPE_HOTPATH | sgm.PIPE_TAPS)
+        c.set_census_window(9, 7)
+        c.configure(w, h, to_sgm_option(opts))
+        got = c.match(left, right)
+        assert_same("9x7 C2 aggr", c.stage("aggr"), want["aggr"])
+        assert_same("9x7 C2 disp_lr", got, want["disp_lr"])
+        with pytest.raises(sgm.SGMError):
+            c.set_census_window(3, 3)
