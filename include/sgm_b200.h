@@ -52,6 +52,8 @@ enum {
     SGMB_STAGE_DISP_SPECKLE  = 6,  /* float  [N]     after speckle removal      SemiGlobalMatching.c:585-642 (needs SGMB_PIPE_TAPS) */
     SGMB_STAGE_DISP_FINAL    = 7,  /* float  [N]     what SGM_Match returns                                   */
     SGMB_STAGE_SPECKLE_LABELS = 8, /* int32  [2*N]   speckle filter scratch: component root per pixel (-1: invalid), then size per root */
+    SGMB_STAGE_GREY_LEFT     = 9,  /* uint8  [N]     grey images the path ran on (after SGMB_MatchFrame: the fused conversion's output) */
+    SGMB_STAGE_GREY_RIGHT    = 10,
     SGMB_STAGE_PATH_PLANE_0  = 16  /* uint8  [N*D]   +r: L_r(p,d) of direction r (order of SemiGlobalMatching.c:213-220) as written by
                                       its regular paths; pixels on an irregular path hold 0 (needs SGMB_PIPE_TAPS) */
 };
@@ -102,6 +104,44 @@ int SGMB_MatchBatchDevice(SGMB_Context* ctx, const uint8_t* const* d_lefts, cons
 int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots_per_device, uint16_t width, uint16_t height,
                             const SGMOption* option, unsigned pipeline_flags, const uint8_t* const* lefts,
                             const uint8_t* const* rights, float* const* disps, int n);
+
+/* ---- The steps either side of the path in the reference system ---- */
+
+/* Colour -> grey weights used by SGMB_MatchFrame*: grey = (wR*R + 150*G + 29*B) >> 8. */
+enum {
+    SGMB_GREY_BOARD = 0,   /* wR = 76: the board's convert_to_gray, ZedBoard/.../src/stereo_matching.c:18-24 (default)      */
+    SGMB_GREY_STB   = 1    /* wR = 77: stb_image's conversion used by the demo's loader, stb_image.h:1746-1749 / main.c:25  */
+};
+int SGMB_SetGreyFormula(SGMB_Context* ctx, int formula);
+
+/* One frame in the board's layout: six planes of width*height bytes, left B,G,R then right B,G,R
+ * (SteroPairImg_t, ZedBoard/.../src/frame_buffer.h:29-41; sent plane by plane by HostScript_Server/server.py:126-131).
+ * The colour -> grey conversion is fused into the census kernel's staging pass.  calib20 == NULL: `out` receives the
+ * disparity map (as SGM_Match).  Otherwise calib20 is the 20-float wire calibration (cam0[9], cam1[9], doffs,
+ * baseline; HostScript_Server/stereo_calibration.py:177-194, frame_buffer.h:16-22) and `out` receives the depth map
+ * baseline*fx/(disparity+doffs) in float32 (HostScript_Server/depth_image.py:138-165), NaN where the disparity is
+ * invalid -- the float32 rows the board replies with (ZedBoard/.../src/tcp_perf_client.c:92-143). */
+int SGMB_MatchFrame(SGMB_Context* ctx, const uint8_t* planes6, const float* calib20, float* out);
+int SGMB_MatchFrameDevice(SGMB_Context* ctx, const uint8_t* d_planes6, const float* calib20, float* d_out, int sync);
+
+/* Wire messages (host only, no CUDA call).  Reply: type byte 3, frame id u32 LE, width u16 LE, height u16 LE, then
+ * width*height float32 (tcp_perf_client.c:106-131; read back by server.py:148-177).  Frame header: '<BiHH' = type
+ * (1: followed by the 80-byte calibration, 2: images only), sequence, width, height (server.py:114); payload_bytes =
+ * what follows the 9 header bytes. */
+size_t SGMB_DepthReplyBytes(uint16_t width, uint16_t height);
+int SGMB_PackDepthReply(uint32_t frame_id, uint16_t width, uint16_t height, const float* depth, uint8_t* dst, size_t capacity);
+int SGMB_ParseFrameHeader(const uint8_t* bytes9, int* type, int32_t* seq, uint16_t* width, uint16_t* height, size_t* payload_bytes);
+
+/* Evaluation step after the path.  depth = baseline*fx/(disp+doffs), float32, numpy's evaluation order
+ * (depth_image.py:138-165); +inf disparities (INVALID_FLOAT) become NaN. */
+int SGMB_DisparityToDepth(SGMB_Context* ctx, const float* disp, size_t n, float baseline, float fx, float doffs, float* depth);
+int SGMB_DisparityToDepthDevice(SGMB_Context* ctx, const float* d_disp, size_t n, float baseline, float fx, float doffs, float* d_depth);
+/* compare_img (depth_image.py:276-319): over pixels where both maps are finite, RMSE and the fraction with
+ * |test - gt| > abs_thresh (the reference's default: 10 mm); (NaN, NaN, 0) when no pixel is valid. */
+int SGMB_CompareDepth(SGMB_Context* ctx, const float* gt, const float* test, size_t n, float abs_thresh, double* rmse,
+                      double* bpr, long long* n_valid);
+int SGMB_CompareDepthDevice(SGMB_Context* ctx, const float* d_gt, const float* d_test, size_t n, float abs_thresh, double* rmse,
+                            double* bpr, long long* n_valid);
 
 /* Copy a retained stage of slot 0 to host memory; `bytes` must equal the stage's size. */
 int SGMB_GetStage(SGMB_Context* ctx, int stage, void* host_dst, size_t bytes);

@@ -240,3 +240,35 @@ def stb_gray(rgb: np.ndarray) -> np.ndarray:
     """stb_image's RGB -> 1-channel conversion used by main.c:25-26 (stb_image.h:1746-1749)."""
     r, g, b = (rgb[..., i].astype(np.uint32) for i in range(3))
     return ((r * 77 + g * 150 + b * 29) >> 8).astype(np.uint8)
+
+
+# ------------------------------------------------------------------ steps either side of the path (SURVEY 8f N3 / N4)
+def board_gray(bgr_planes: np.ndarray) -> np.ndarray:
+    """The board's colour -> grey conversion, ZedBoard/Vitis/lwip_tcp_perf_client/src/stereo_matching.c:18-24:
+    (76*R + 150*G + 29*B) >> 8 on planar B,G,R input [3, H, W]."""
+    b, g, r = (bgr_planes[i].astype(np.uint32) for i in range(3))
+    return ((76 * r + 150 * g + 29 * b) >> 8).astype(np.uint8)
+
+
+def stb_gray_planar(bgr_planes: np.ndarray) -> np.ndarray:
+    """stb_image's weights (stb_image.h:1746-1749) on planar B,G,R input."""
+    return stb_gray(np.stack([bgr_planes[2], bgr_planes[1], bgr_planes[0]], axis=-1))
+
+
+def disparity_to_depth(disp: np.ndarray, baseline: float, fx: float, doffs: float) -> np.ndarray:
+    """HostScript_Server/depth_image.py:138-165 restated: float32 throughout (cam matrices are float32 arrays,
+    stereo_calibration.py:38; Python floats are weak scalars), depth = fl(fl(baseline*fx) / fl(disp + doffs)).
+    Pinned by tests/golden/eval_depth.npz, generated from the reference module itself."""
+    d = np.asarray(disp, np.float32)
+    bf = np.float32(baseline) * np.float32(fx)
+    return (bf / (d + np.float32(doffs))).astype(np.float32)
+
+
+def compare_img(ground_truth: np.ndarray, test: np.ndarray, abs_thresh: float = 10.0):
+    """HostScript_Server/depth_image.py:276-319 restated: (rmse, bpr, n_valid) over pixels finite in both maps."""
+    valid = np.isfinite(test) & np.isfinite(ground_truth)
+    n = int(np.count_nonzero(valid))
+    if n == 0:
+        return float("nan"), float("nan"), 0
+    diff = test[valid] - ground_truth[valid]
+    return float(np.sqrt(np.mean(np.square(diff)))), float(np.count_nonzero(np.abs(diff) > abs_thresh) / n), n

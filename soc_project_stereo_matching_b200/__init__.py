@@ -34,6 +34,8 @@ STAGES = {  # name -> (id, dtype, per-pixel depth: 1 or "D")
     "disp_speckle": (6, np.float32, 1), "disp_final": (7, np.float32, 1),
 }
 STAGE_PATH_PLANE_0 = 16
+STAGE_GREY_LEFT, STAGE_GREY_RIGHT = 9, 10
+GREY_BOARD, GREY_STB = 0, 1     # (76R+150G+29B)>>8 (board) / (77R+150G+29B)>>8 (stb_image, the demo's loader)
 
 
 class SGMOption(C.Structure):
@@ -83,6 +85,16 @@ def _load() -> C.CDLL:
         "SGMB_MatchBatchDevice": (i32, [vp, vp, vp, vp, i32]),
         "SGMB_MatchBatchMultiGPU": (i32, [vp, i32, i32, u16, u16, C.POINTER(SGMOption), C.c_uint, vp, vp, vp, i32]),
         "SGMB_GetStage": (i32, [vp, i32, vp, C.c_size_t]),
+        "SGMB_SetGreyFormula": (i32, [vp, i32]),
+        "SGMB_MatchFrame": (i32, [vp, vp, vp, vp]),
+        "SGMB_MatchFrameDevice": (i32, [vp, vp, vp, vp, i32]),
+        "SGMB_DepthReplyBytes": (C.c_size_t, [u16, u16]),
+        "SGMB_PackDepthReply": (i32, [C.c_uint32, u16, u16, vp, vp, C.c_size_t]),
+        "SGMB_ParseFrameHeader": (i32, [vp, C.POINTER(i32), C.POINTER(C.c_int32), C.POINTER(u16), C.POINTER(u16), C.POINTER(C.c_size_t)]),
+        "SGMB_DisparityToDepth": (i32, [vp, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, vp]),
+        "SGMB_DisparityToDepthDevice": (i32, [vp, vp, C.c_size_t, C.c_float, C.c_float, C.c_float, vp]),
+        "SGMB_CompareDepth": (i32, [vp, vp, vp, C.c_size_t, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+        "SGMB_CompareDepthDevice": (i32, [vp, vp, vp, C.c_size_t, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
         "SGMB_HostAlloc": (i32, [C.POINTER(vp), C.c_size_t]),
         "SGMB_HostFree": (None, [vp]),
         "SGMB_KernelLaunchesPerFrame": (i32, [vp]),
@@ -264,6 +276,43 @@ class Context:
         _check(lib.SGMB_GetStage(self._h, sid, out.ctypes.data, out.nbytes))
         return out
 
+    # ---- frame formats either side of the path and evaluation (N4)
+    def set_grey_formula(self, formula: int) -> None:
+        _check(lib.SGMB_SetGreyFormula(self._h, formula))
+
+    def match_frame(self, planes6: np.ndarray, calib20: np.ndarray | None = None) -> np.ndarray:
+        """planes6: uint8 [6, H, W] = left B,G,R then right B,G,R (the board's frame layout).  Returns the
+        disparity map, or the depth map when the 20-float wire calibration is given."""
+        p = np.ascontiguousarray(planes6, np.uint8)
+        if p.shape != (6, self.height, self.width):
+            raise ValueError("planes6 must have shape (6, H, W)")
+        cal = None if calib20 is None else np.ascontiguousarray(calib20, np.float32)
+        if cal is not None and cal.size != 20:
+            raise ValueError("calib20 must hold 20 floats")
+        out = np.empty((self.height, self.width), np.float32)
+        _check(lib.SGMB_MatchFrame(self._h, p.ctypes.data, cal.ctypes.data if cal is not None else None, out.ctypes.data))
+        return out
+
+    def grey(self, right: bool = False) -> np.ndarray:
+        out = np.empty((self.height, self.width), np.uint8)
+        _check(lib.SGMB_GetStage(self._h, STAGE_GREY_RIGHT if right else STAGE_GREY_LEFT, out.ctypes.data, out.nbytes))
+        return out
+
+    def disparity_to_depth(self, disp: np.ndarray, baseline: float, fx: float, doffs: float) -> np.ndarray:
+        d = np.ascontiguousarray(disp, np.float32)
+        out = np.empty_like(d)
+        _check(lib.SGMB_DisparityToDepth(self._h, d.ctypes.data, d.size, baseline, fx, doffs, out.ctypes.data))
+        return out
+
+    def compare_depth(self, ground_truth: np.ndarray, test: np.ndarray, abs_thresh: float = 10.0):
+        """-> (rmse, bad-pixel rate, n_valid) like HostScript_Server/depth_image.py compare_img."""
+        g = np.ascontiguousarray(ground_truth, np.float32); t = np.ascontiguousarray(test, np.float32)
+        if g.shape != t.shape:
+            raise ValueError("shape mismatch")
+        rmse, bpr, nv = C.c_double(), C.c_double(), C.c_longlong()
+        _check(lib.SGMB_CompareDepth(self._h, g.ctypes.data, t.ctypes.data, g.size, abs_thresh, C.byref(rmse), C.byref(bpr), C.byref(nv)))
+        return rmse.value, bpr.value, nv.value
+
     def speckle_labels(self):
         """Debug tap: (root per pixel or -1, size per root) of the speckle filter's last run."""
         out = np.empty((2, self.height, self.width), np.int32)
@@ -330,3 +379,21 @@ def debug_classify_paths(width: int, height: int, direction: int) -> np.ndarray:
     if n < 0:
         raise SGMError(n)
     return buf
+
+
+def pack_depth_reply(frame_id: int, depth: np.ndarray) -> bytes:
+    """The board's reply message (zb/tcp_perf_client.c:106-131): b'\x03' + '<IHH' + float32 rows."""
+    d = np.ascontiguousarray(depth, np.float32)
+    h, w = d.shape
+    n = lib.SGMB_DepthReplyBytes(w, h)
+    buf = (C.c_uint8 * n)()
+    _check(lib.SGMB_PackDepthReply(frame_id, w, h, d.ctypes.data, buf, n))
+    return bytes(buf)
+
+
+def parse_frame_header(header9: bytes):
+    """-> (type, seq, width, height, payload_bytes) of the server's '<BiHH' frame header (server.py:114)."""
+    b = (C.c_uint8 * 9)(*header9[:9])
+    t, q, w, h, pb = C.c_int(), C.c_int32(), C.c_uint16(), C.c_uint16(), C.c_size_t()
+    _check(lib.SGMB_ParseFrameHeader(b, C.byref(t), C.byref(q), C.byref(w), C.byref(h), C.byref(pb)))
+    return t.value, q.value, w.value, h.value, pb.value

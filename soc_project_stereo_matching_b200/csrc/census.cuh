@@ -15,6 +15,12 @@
 //           cR[q-k]; picking the copy with (padF + a + q - (n-1)) % K == 0 turns that window into
 //           aligned 64/128-bit loads for every pixel position q.
 // The image tile (+ halo) is staged in shared memory.
+//
+// PLANAR = true fuses the colour -> grey conversion of the board's frame format into the staging pass: the
+// input of each view is three planes B, G, R of N bytes (zb/frame_buffer.h:29-41, sent plane by plane by
+// host/server.py:126-131), grey = (wR*R + wG*G + wB*B) >> 8 with the board's weights 76/150/29
+// (zb/stereo_matching.c:18-24) or stb_image's 77/150/29 (stb_image.h:1746-1749, what main.c's loader applies);
+// the grey tile feeds the census directly and its interior is also written out (K2 needs the left grey image).
 #pragma once
 
 #include <stdint.h>
@@ -22,7 +28,9 @@
 namespace sgmb {
 
 struct CensusParams {
-    const uint8_t* img[2];   // left, right
+    const uint8_t* img[2];   // left, right: grey [N], or planar B,G,R [3][N] when PLANAR
+    uint8_t* grey[2];        // PLANAR only: converted grey images [N]
+    uint32_t wR, wG, wB;     // PLANAR only: grey = (wR*R + wG*G + wB*B) >> 8
     void* left;              // DT [N]
     void* right4;            // DT [K][copyStride]
     size_t copyStride;       // elements per copy (padF + N + padB, multiple of 4)
@@ -33,7 +41,7 @@ struct CensusParams {
 constexpr int kCensusTileW = 64;
 constexpr int kCensusTileH = 8;
 
-template <int CW, int CH, typename DT>
+template <int CW, int CH, typename DT, bool PLANAR>
 __global__ void __launch_bounds__(kCensusTileW * kCensusTileH / 2)
 sgm_census(CensusParams P)
 {
@@ -49,7 +57,19 @@ sgm_census(CensusParams P)
     for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
         const int ty = i / TW, tx = i % TW;
         const int y = y0 + ty - RY, x = x0 + tx - RX;
-        tile[ty][tx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + (size_t)y * W + x) : 0;
+        uint8_t v = 0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const size_t p = (size_t)y * W + x;
+            if (PLANAR) {
+                const size_t N = (size_t)W * H;
+                v = (uint8_t)((P.wB * __ldg(img + p) + P.wG * __ldg(img + N + p) + P.wR * __ldg(img + 2 * N + p)) >> 8);
+                // each pixel belongs to the interior of exactly one tile
+                if (ty >= RY && ty < RY + kCensusTileH && tx >= RX && tx < RX + kCensusTileW) P.grey[which][p] = v;
+            } else {
+                v = __ldg(img + p);
+            }
+        }
+        tile[ty][tx] = v;
     }
     __syncthreads();
 

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -20,6 +21,7 @@
 #include "../../include/sgm_b200.h"
 #include "aggregate.cuh"
 #include "census.cuh"
+#include "frontend.cuh"
 #include "path_walker.h"
 #include "postproc.cuh"
 #include "wta.cuh"
@@ -67,6 +69,8 @@ struct Slot {
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
     unsigned long long* xchg = nullptr;   // median wavefront exchange rows [(H+31)/32][W]
     float* medianPrep = nullptr;      // sorted unfiltered inputs in wavefront order (postproc.cuh K5a)
+    uint8_t* framePlanes = nullptr;   // SGMB_MatchFrame: left B,G,R then right B,G,R planes [6][N] (allocated on first use)
+    float* depth = nullptr;           // SGMB_MatchFrame with calibration: depth map [N] (allocated on first use)
     unsigned medianEpoch = 0;
     bool busy = false;
 };
@@ -81,6 +85,8 @@ struct SGMB_Context {
     int W = 0, H = 0, D = 0, Dp = 0, NR = 0, nDirs = 8;
     int censusW = 5, censusH = 5;     // requested window (SGMB_SetCensusWindow); takes effect at SGMB_Configure
     int descBytes = 4;                // descriptor size of the current configuration: 4 (5x5) or 8 (9x7)
+    int greyFormula = SGMB_GREY_BOARD; // SGMB_MatchFrame: weights of the colour -> grey conversion
+    CompareAcc* cmpScratch = nullptr; // SGMB_CompareDepth*: per-block partials + result
     size_t N = 0;
     int padF = 0;
     size_t copyStride = 0, planeStride = 0;
@@ -113,6 +119,7 @@ static void free_slot_buffers(Slot& s)
 {
     cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
+    cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
     cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
     s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr;
@@ -166,6 +173,7 @@ extern "C" void SGMB_Destroy(SGMB_Context* c)
     cudaDeviceSynchronize();
     free_config(c);
     cudaFree(c->flushBuf);
+    cudaFree(c->cmpScratch);
     for (auto& s : c->slots) {
         if (s.evStart) cudaEventDestroy(s.evStart);
         if (s.evStop) cudaEventDestroy(s.evStop);
@@ -404,7 +412,9 @@ extern "C" int SGMB_SetPipeline(SGMB_Context* c, unsigned flags)
 // ------------------------------------------------------------------------------------------------ one frame
 // Enqueue the whole pipeline on the slot's stream.  dL/dR: device images; result left in slot.dispFinal
 // (or dOut when given).  Returns the number of kernels launched through *launches.
-static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint8_t* dR, float* dOut, bool timeAgg, int* launches)
+//   planar: dL / dR are planar B,G,R frames [3][N]; the census kernel converts them to grey on the fly (into s.img[]).
+static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint8_t* dR, float* dOut, bool timeAgg, int* launches,
+                         bool planar = false)
 {
     const int W = c->W, H = c->H, D = c->D;
     const bool taps = (c->pipeline & SGMB_PIPE_TAPS) != 0;
@@ -418,10 +428,19 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         CensusParams p{};
         p.img[0] = dL; p.img[1] = dR; p.left = s.censusL; p.right4 = s.censusR4;
         p.copyStride = c->copyStride; p.padF = c->padF; p.W = W; p.H = H;
+        p.grey[0] = s.img[0]; p.grey[1] = s.img[1];
+        p.wR = (c->greyFormula == SGMB_GREY_STB) ? 77u : 76u; p.wG = 150u; p.wB = 29u;
         dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
-        if (c->descBytes == 4) sgm_census<5, 5, uint32_t><<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
-        else                   sgm_census<9, 7, desc64_t><<<grid, kCensusTileW * kCensusTileH / 2, 0, s.stream>>>(p);
+        const int threads = kCensusTileW * kCensusTileH / 2;
+        if (c->descBytes == 4) {
+            if (planar) sgm_census<5, 5, uint32_t, true><<<grid, threads, 0, s.stream>>>(p);
+            else        sgm_census<5, 5, uint32_t, false><<<grid, threads, 0, s.stream>>>(p);
+        } else {
+            if (planar) sgm_census<9, 7, desc64_t, true><<<grid, threads, 0, s.stream>>>(p);
+            else        sgm_census<9, 7, desc64_t, false><<<grid, threads, 0, s.stream>>>(p);
+        }
         ++nk;
+        if (planar) dL = s.img[0];       // K2 reads the left grey image (adaptive P2, SemiGlobalMatching.c:335)
     }
     {   // K2 aggregation
         AggParams p{};
@@ -616,6 +635,179 @@ extern "C" int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots, 
     return SGMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ frame formats (N3) and evaluation (N4)
+extern "C" int SGMB_SetGreyFormula(SGMB_Context* c, int formula)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if (formula != SGMB_GREY_BOARD && formula != SGMB_GREY_STB) return fail(SGMB_E_ARG, "SGMB_SetGreyFormula: unknown formula %d", formula);
+    c->greyFormula = formula;
+    return SGMB_OK;
+}
+
+static int launch_depth(SGMB_Context* c, const float* dDisp, float* dDepth, size_t n, float baseline, float fx, float doffs, cudaStream_t st)
+{
+    const float bf = baseline * fx;                       // float32 product, as numpy forms it (depth_image.py:163)
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    sgm_disparity_to_depth<<<std::max(blocks, 1), 256, 0, st>>>(dDisp, dDepth, n, bf, doffs);
+    CU(cudaGetLastError());
+    (void)c;
+    return SGMB_OK;
+}
+
+// One frame in the board's layout: six planes left B,G,R, right B,G,R (zb/frame_buffer.h:29-41).  calib20 == NULL:
+// the result is the disparity map; otherwise it is the 20-float wire calibration (cam0, cam1 row-major, doffs,
+// baseline; HostScript_Server/stereo_calibration.py:177-194) and the result is depth (depth_image.py:138-165).
+static int match_frame(SGMB_Context* c, const uint8_t* planes6, const float* calib20, float* out, bool deviceMem, int sync)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_MatchFrame: context is not configured");
+    if (!planes6 || !out) return fail(SGMB_E_ARG, "SGMB_MatchFrame: NULL pointer");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    const size_t N = c->N;
+    CU(cudaEventRecord(s.evStart, s.stream));
+    const uint8_t* dPlanes = planes6;
+    if (!deviceMem) {
+        if (!s.framePlanes) CU(cudaMalloc(&s.framePlanes, 6 * N + 16));
+        CU(cudaMemcpyAsync(s.framePlanes, planes6, 6 * N, cudaMemcpyHostToDevice, s.stream));
+        dPlanes = s.framePlanes;
+    }
+    if (int rc = enqueue_frame(c, s, dPlanes, dPlanes + 3 * N, nullptr, false, nullptr, true)) return rc;
+    const float* result = frame_result(c, s);
+    if (calib20) {
+        if (!s.depth) CU(cudaMalloc(&s.depth, N * sizeof(float)));
+        if (int rc = launch_depth(c, result, s.depth, N, calib20[19], calib20[0], calib20[18], s.stream)) return rc;
+        result = s.depth;
+    }
+    CU(cudaMemcpyAsync(out, result, N * sizeof(float), deviceMem ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaEventRecord(s.evStop, s.stream));
+    if (sync) {
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+    }
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_MatchFrame(SGMB_Context* c, const uint8_t* planes6, const float* calib20, float* out)
+{
+    return match_frame(c, planes6, calib20, out, false, 1);
+}
+
+extern "C" int SGMB_MatchFrameDevice(SGMB_Context* c, const uint8_t* d_planes6, const float* calib20, float* d_out, int sync)
+{
+    return match_frame(c, d_planes6, calib20, d_out, true, sync);
+}
+
+extern "C" size_t SGMB_DepthReplyBytes(uint16_t width, uint16_t height) { return 9 + (size_t)width * height * sizeof(float); }
+
+// Reply message of the board (zb/tcp_perf_client.c:106-131, parsed by HostScript_Server/server.py:148-177):
+// type byte 3, frame id (32-bit LE), width, height (16-bit LE), then width*height float32 rows.
+extern "C" int SGMB_PackDepthReply(uint32_t frame_id, uint16_t width, uint16_t height, const float* depth, uint8_t* dst, size_t capacity)
+{
+    const size_t need = SGMB_DepthReplyBytes(width, height);
+    if (!depth || !dst) return fail(SGMB_E_ARG, "SGMB_PackDepthReply: NULL pointer");
+    if (capacity < need) return fail(SGMB_E_STATE, "SGMB_PackDepthReply: needs %zu bytes, got %zu", need, capacity);
+    dst[0] = 3;
+    for (int i = 0; i < 4; ++i) dst[1 + i] = (uint8_t)(frame_id >> (8 * i));
+    dst[5] = (uint8_t)width; dst[6] = (uint8_t)(width >> 8);
+    dst[7] = (uint8_t)height; dst[8] = (uint8_t)(height >> 8);
+    memcpy(dst + 9, depth, need - 9);
+    return SGMB_OK;
+}
+
+// Frame header sent by the server: '<BiHH' = type (1: with 80-byte calibration, 2: images only), sequence
+// number, width, height (HostScript_Server/server.py:114; parsed at zb/tcp_perf_client.c:154-201).
+extern "C" int SGMB_ParseFrameHeader(const uint8_t* bytes9, int* type, int32_t* seq, uint16_t* width, uint16_t* height, size_t* payload_bytes)
+{
+    if (!bytes9) return fail(SGMB_E_ARG, "SGMB_ParseFrameHeader: NULL pointer");
+    const int t = bytes9[0];
+    if (t != 1 && t != 2) return fail(SGMB_E_ARG, "SGMB_ParseFrameHeader: message type %d carries no frame", t);
+    const uint32_t q = (uint32_t)bytes9[1] | ((uint32_t)bytes9[2] << 8) | ((uint32_t)bytes9[3] << 16) | ((uint32_t)bytes9[4] << 24);
+    const uint16_t w = (uint16_t)(bytes9[5] | (bytes9[6] << 8)), h = (uint16_t)(bytes9[7] | (bytes9[8] << 8));
+    if (type) *type = t;
+    if (seq) *seq = (int32_t)q;
+    if (width) *width = w;
+    if (height) *height = h;
+    if (payload_bytes) *payload_bytes = (t == 1 ? 80 : 0) + (size_t)6 * w * h;
+    return SGMB_OK;
+}
+
+static int depth_convert(SGMB_Context* c, const float* disp, size_t n, float baseline, float fx, float doffs, float* depth, bool deviceMem)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if ((!disp || !depth) && n) return fail(SGMB_E_ARG, "SGMB_DisparityToDepth: NULL pointer");
+    if (n == 0) return SGMB_OK;
+    if (int rc = ensure_device(c)) return rc;
+    cudaStream_t st = c->slots[0].stream;
+    if (deviceMem) {
+        if (int rc = launch_depth(c, disp, depth, n, baseline, fx, doffs, st)) return rc;
+        CU(cudaStreamSynchronize(st));
+        return SGMB_OK;
+    }
+    float* d = nullptr;
+    CU(cudaMalloc(&d, n * sizeof(float)));
+    int rc = SGMB_OK;
+    cudaError_t e = cudaMemcpyAsync(d, disp, n * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = launch_depth(c, d, d, n, baseline, fx, doffs, st);
+    if (e == cudaSuccess && rc == SGMB_OK) e = cudaMemcpyAsync(depth, d, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SGMB_E_CUDA, "SGMB_DisparityToDepth: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int SGMB_DisparityToDepth(SGMB_Context* c, const float* disp, size_t n, float baseline, float fx, float doffs, float* depth)
+{
+    return depth_convert(c, disp, n, baseline, fx, doffs, depth, false);
+}
+
+extern "C" int SGMB_DisparityToDepthDevice(SGMB_Context* c, const float* d_disp, size_t n, float baseline, float fx, float doffs, float* d_depth)
+{
+    return depth_convert(c, d_disp, n, baseline, fx, doffs, d_depth, true);
+}
+
+static int compare_depth(SGMB_Context* c, const float* gt, const float* test, size_t n, float thresh, double* rmse, double* bpr,
+                         long long* nValid, bool deviceMem)
+{
+    if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if ((!gt || !test) && n) return fail(SGMB_E_ARG, "SGMB_CompareDepth: NULL pointer");
+    if (int rc = ensure_device(c)) return rc;
+    cudaStream_t st = c->slots[0].stream;
+    if (!c->cmpScratch) CU(cudaMalloc(&c->cmpScratch, (kCompareBlocks + 1) * sizeof(CompareAcc)));
+    float* tmp = nullptr;
+    const float *dG = gt, *dT = test;
+    if (!deviceMem && n) {
+        CU(cudaMalloc(&tmp, 2 * n * sizeof(float)));
+        cudaError_t e = cudaMemcpyAsync(tmp, gt, n * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + n, test, n * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { cudaFree(tmp); return fail(SGMB_E_CUDA, "SGMB_CompareDepth: %s", cudaGetErrorString(e)); }
+        dG = tmp; dT = tmp + n;
+    }
+    sgm_compare_depth_partial<<<kCompareBlocks, kCompareThreads, 0, st>>>(dG, dT, n, thresh, c->cmpScratch);
+    sgm_compare_depth_final<<<1, 32, 0, st>>>(c->cmpScratch, kCompareBlocks, c->cmpScratch + kCompareBlocks);
+    CompareAcc acc{};
+    cudaError_t e = cudaMemcpyAsync(&acc, c->cmpScratch + kCompareBlocks, sizeof acc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(SGMB_E_CUDA, "SGMB_CompareDepth: %s", cudaGetErrorString(e));
+    // depth_image.py:300-302: no valid pixel -> (nan, nan, 0)
+    if (nValid) *nValid = (long long)acc.nValid;
+    if (rmse) *rmse = acc.nValid ? sqrt(acc.sumSq / (double)acc.nValid) : NAN;
+    if (bpr) *bpr = acc.nValid ? (double)acc.nBad / (double)acc.nValid : NAN;
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_CompareDepth(SGMB_Context* c, const float* gt, const float* test, size_t n, float abs_thresh, double* rmse,
+                                 double* bpr, long long* n_valid)
+{
+    return compare_depth(c, gt, test, n, abs_thresh, rmse, bpr, n_valid, false);
+}
+
+extern "C" int SGMB_CompareDepthDevice(SGMB_Context* c, const float* d_gt, const float* d_test, size_t n, float abs_thresh, double* rmse,
+                                       double* bpr, long long* n_valid)
+{
+    return compare_depth(c, d_gt, d_test, n, abs_thresh, rmse, bpr, n_valid, true);
+}
+
 // ------------------------------------------------------------------------------------------------ taps
 extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes)
 {
@@ -641,6 +833,8 @@ extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes
             need = N * 4; break;
         case SGMB_STAGE_DISP_FINAL:    src = frame_result(c, s); need = N * 4; break;
         case SGMB_STAGE_SPECKLE_LABELS: src = s.labels; need = 2 * N * 4; break;
+        case SGMB_STAGE_GREY_LEFT:     src = s.img[0]; need = N; break;
+        case SGMB_STAGE_GREY_RIGHT:    src = s.img[1]; need = N; break;
         default:
             if (stage >= SGMB_STAGE_PATH_PLANE_0 && stage < SGMB_STAGE_PATH_PLANE_0 + c->nDirs) {
                 need = N * c->D;
