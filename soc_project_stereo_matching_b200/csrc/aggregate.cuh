@@ -157,6 +157,14 @@ template <int LPP>
 __device__ __forceinline__ uint32_t group_min_x2(uint32_t m)               // m: both fields equal
 {
     if (LPP == 32) return __reduce_min_sync(0xffffffffu, m);
+    if (LPP == 16) {
+        // two warp-wide CREDUX.MIN with the other half-warp masked to 0xFFFFFFFF: 44 cycles in a dependent chain
+        // against 132 for the four-round shuffle butterfly (scripts/micro/groupmin.cu, measured on B200)
+        const bool hi = (threadIdx.x & 16) != 0;
+        const uint32_t a = __reduce_min_sync(0xffffffffu, hi ? 0xffffffffu : m);
+        const uint32_t b = __reduce_min_sync(0xffffffffu, hi ? m : 0xffffffffu);
+        return hi ? b : a;
+    }
 #pragma unroll
     for (int o = LPP / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(0xffffffffu, m, o));
     return m;
@@ -265,7 +273,7 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
     }
 }
 
-template <int NR, int LPP, bool FWD, typename DT>
+template <int NR, int LPP, bool FWD, typename DT, bool PAD>
 __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
@@ -280,7 +288,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int i0 = DPL * sub + 2 * r;
-        padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
     }
     const int dbase = P.dmin + DPL * sub;
     const int dlast = P.dmin + LPP * DPL - 1;
@@ -359,7 +367,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 // with a constant stride (plus one column wrap for diagonals); 32/LPP paths of one direction share a warp and
 // every lane owns 2*NR disparities.  The loads of visit s+1 are issued before the dependent chain of visit s
 // (two input buffers, loop unrolled by two).
-template <int NR, int LPP, bool DIAG, typename DT>
+template <int NR, int LPP, bool DIAG, typename DT, bool PAD>
 __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const WarpWork job, int lane)
 {
     static_assert(NR == 1 || NR == 2 || NR == 4 || NR == 8, "NR");
@@ -381,7 +389,7 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int i0 = DPL * sub + 2 * r;
-        padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
     }
     const int dbase = P.dmin + DPL * sub;                 // absolute disparity of this lane's first index
     const int dlast = P.dmin + DPL * LPP - 1;             // largest absolute disparity the group may hold
@@ -458,7 +466,7 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
 // ------------------------------------------------------------------------------------------------ irregular paths
 // Generic walker (path_walker.h), one path per warp; results are added to the side buffer because an
 // irregular path visits pixels that a regular path also writes.
-template <int NR, typename DT>
+template <int NR, typename DT, bool PAD>
 __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
@@ -468,7 +476,7 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int i0 = DPL * lane + 2 * r;
-        padm[r] = (i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u);
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
     }
     const int dbase = P.dmin + DPL * lane;
     const bool lane_stores = DPL * lane < P.Dp;
@@ -532,7 +540,10 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
 
 // NRH/LPPH: layout of the horizontal directions (latency-critical: H paths of W steps);
 // NRV/LPPV: layout of the vertical and diagonal directions; NRI: layout of irregular paths (32 lanes).
-template <int NRH, int LPPH, int NRV, int LPPV, int NRI, typename DT>
+// PAD = false: the disparity range fills every lane of every layout exactly (D == LPPH*2*NRH == LPPV*2*NRV ==
+// 64*NRI), so the masks that park unused disparity slots at 255 vanish (they cost ~50 of ~220 instructions per
+// visit when the compiler rematerialises them in the loop).
+template <int NRH, int LPPH, int NRV, int LPPV, int NRI, typename DT, bool PAD>
 __global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
 sgm_aggregate_paths(const __grid_constant__ AggParams P)
 {
@@ -540,11 +551,11 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
     const int lane = threadIdx.x & 31;
     if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
     const WarpWork job = P.work[widx];
-    if (widx < P.nIrregularWarps) aggregate_irregular<NRI, DT>(P, job, lane);
-    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT>(P, job, lane);
-    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT>(P, job, lane);
-    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT>(P, job, lane);
-    else                          aggregate_column_like<NRV, LPPV, true, DT>(P, job, lane);
+    if (widx < P.nIrregularWarps) aggregate_irregular<NRI, DT, PAD>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT, PAD>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD>(P, job, lane);
+    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT, PAD>(P, job, lane);
+    else                          aggregate_column_like<NRV, LPPV, true, DT, PAD>(P, job, lane);
 }
 
 }  // namespace sgmb

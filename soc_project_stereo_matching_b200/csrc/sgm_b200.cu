@@ -95,6 +95,7 @@ struct SGMB_Context {
     int nIrregularWarps = 0, nRegularWarps = 0;
     int lppV = 8;                 // lanes per path of the vertical / diagonal directions
     int lppH = 16;                // lanes per path of the horizontal directions
+    int altLayout = 0;            // SGM_B200_DEBUG_LAYOUT: alternative kernel layouts for experiments
     int32_t* entryOf = nullptr;
     int nEntries = 0, nIrregular = 0;
     uint32_t p2x2[256] = {};
@@ -296,6 +297,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     //      64-bit descriptors double the registers of the prefetched census windows, so that mode keeps 8
     //      disparities per lane up to D = 128 (must match the template arguments in enqueue_frame).
     c->lppV = (D <= 128 && !(c->descBytes == 8 && D > 64)) ? 8 : 16;
+    c->altLayout = getenv("SGM_B200_DEBUG_LAYOUT") ? atoi(getenv("SGM_B200_DEBUG_LAYOUT")) : 0;   // experiments only
+    if (c->altLayout == 1 && c->descBytes == 4 && c->NR == 2) c->lppV = 16;
     c->lppH = 16;
     const int perWarpV = 32 / c->lppV, perWarpH = 32 / c->lppH;
     std::vector<WarpWork> irregular, regular;
@@ -453,15 +456,24 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
         const int threads = kAggWarpsPerBlock * 32;
         if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
+        // PAD = false when the disparity range fills every lane of every layout exactly (see aggregate.cuh)
+        const bool pad = (D != 64 * c->NR) || (c->altLayout == 2);
+#define SGM_AGG_LAUNCH(NRH, LPPH, NRV, LPPV, NRI, DT)                                                          \
+    do {                                                                                                       \
+        if (pad) sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, true><<<blocks, threads, 0, s.stream>>>(p);  \
+        else     sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, false><<<blocks, threads, 0, s.stream>>>(p); \
+    } while (0)
         if (c->descBytes == 4) {
-            if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
-            else if (c->NR == 2) sgm_aggregate_paths<4, 16, 8, 8, 2, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
-            else                 sgm_aggregate_paths<8, 16, 8, 16, 4, uint32_t><<<blocks, threads, 0, s.stream>>>(p);
+            if (c->NR == 1)                           SGM_AGG_LAUNCH(2, 16, 4, 8, 1, uint32_t);
+            else if (c->NR == 2 && c->altLayout == 1) SGM_AGG_LAUNCH(4, 16, 4, 16, 2, uint32_t);
+            else if (c->NR == 2)                      SGM_AGG_LAUNCH(4, 16, 8, 8, 2, uint32_t);
+            else                                      SGM_AGG_LAUNCH(8, 16, 8, 16, 4, uint32_t);
         } else {
-            if (c->NR == 1)      sgm_aggregate_paths<2, 16, 4, 8, 1, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
-            else if (c->NR == 2) sgm_aggregate_paths<4, 16, 4, 16, 2, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
-            else                 sgm_aggregate_paths<8, 16, 8, 16, 4, desc64_t><<<blocks, threads, 0, s.stream>>>(p);
+            if (c->NR == 1)      SGM_AGG_LAUNCH(2, 16, 4, 8, 1, desc64_t);
+            else if (c->NR == 2) SGM_AGG_LAUNCH(4, 16, 4, 16, 2, desc64_t);
+            else                 SGM_AGG_LAUNCH(8, 16, 8, 16, 4, desc64_t);
         }
+#undef SGM_AGG_LAUNCH
         if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
         ++nk;
     }
