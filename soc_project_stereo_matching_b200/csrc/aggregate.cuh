@@ -62,6 +62,7 @@ struct AggParams {
     const WarpWork* work;       // [nIrregularWarps] irregular jobs, then [nRegularWarps] regular jobs
     int nIrregularWarps, nRegularWarps;
     int W, H, D, Dp, dmin;
+    int wrapInterior;           // 1: a visit without out-of-image costs can still exceed 255 (largest census cost + largest P2 > 255)
     uint32_t p1x2;              // min(P1, 256) in both 16-bit fields
     uint32_t p2x2[256];         // min(256, max(P1, P2_init/(delta+1))) in both fields, indexed by |g - gPrev|
 };
@@ -121,13 +122,15 @@ __device__ __forceinline__ void pack_cost(const StepInput<NR, DT>& in, int nvali
             c0 = (2 * r < nvalid) ? c0 : 127u;
             c1 = (2 * r + 1 < nvalid) ? c1 : 127u;
         }
-        C[r] = c1 * 65536u + c0;
+        C[r] = __byte_perm(c0, c1, 0x5410);
     }
 }
 
 // One DP step on the lane's registers.  up / dn: the neighbouring lanes' edge registers (sentinel 0x00FF00FF
 // at the ends of the disparity range).
-template <int NR>
+// WRAP = false: the caller guarantees C + (m - minPrev) <= 255 in every field (no cost of 127 in this visit and
+// max cost + largest P2 <= 255, AggParams::wrapInterior == 0), so the reference's uint8 truncation is the identity.
+template <int NR, bool WRAP = true>
 __device__ __forceinline__ void dp_step(uint32_t (&L)[NR], const uint32_t (&C)[NR], const uint32_t (&padm)[NR],
                                         uint32_t up, uint32_t dn, uint32_t p1x2, uint32_t p2x2, uint32_t negmin)
 {
@@ -139,7 +142,8 @@ __device__ __forceinline__ void dp_step(uint32_t (&L)[NR], const uint32_t (&C)[N
         uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[r]);                    // min(Lp[d-1]+P1, Lp[d])
         t = __viaddmin_u16x2(lp1, p1x2, t);                                // min(Lp[d+1]+P1, .)
         t = __viaddmin_u16x2(t, negmin, p2x2);                             // min(. - minPrev, P2')   in [0, 255]
-        L[r] = (__vadd2(C[r], t) & 0x00FF00FFu) | padm[r];                 // (uint8)(C + m - minPrev)
+        const uint32_t sum = C[r] + t;                                     // fields <= 127 + 255: no carry between them
+        L[r] = (WRAP ? (sum & 0x00FF00FFu) : sum) | padm[r];               // (uint8)(C + m - minPrev)
         lm1 = lp1;
     }
 }
@@ -208,37 +212,55 @@ struct HorizontalState {
 };
 
 // Prepare step with column x: broadcast its pixel from lane j of the group's block registers, slide the window, cost.
+// ROT >= 0: the window is kept as a ring in its registers -- logical element k lives in register (k -+ t) mod DPL at
+// chunk time t -- so that inside a fully unrolled chunk of DPL steps the slide costs no register moves; ROT is the
+// chunk time BEFORE this slide (after DPL slides logical == physical again).  ROT < 0: plain shifting registers.
 template <int NR, int LPP, bool FWD, bool BORDER, typename DT>
 __device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD, DT>& st, uint32_t gBlk, DT clBlk,
-                                                   DT crBlk, int j, int x, int sub, int dbase)
+                                                   DT crBlk, int j, int x, int sub, int dbase, int ROT)
 {
     constexpr int DPL = 2 * NR;
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t g = __shfl_sync(FULL, gBlk, j, LPP);
     const DT cl = __shfl_sync(FULL, clBlk, j, LPP);
     const DT fresh = __shfl_sync(FULL, crBlk, j, LPP);
-    if (FWD) {
-        DT t = __shfl_up_sync(FULL, st.w[DPL - 1], 1, LPP);
+    int base = 0;                                       // register of logical element 0 after the slide
+    if (ROT < 0) {
+        if (FWD) {
+            DT t = __shfl_up_sync(FULL, st.w[DPL - 1], 1, LPP);
+            if (sub == 0) t = fresh;
+#pragma unroll
+            for (int k = DPL - 1; k > 0; --k) st.w[k] = st.w[k - 1];
+            st.w[0] = t;
+        } else {
+            DT t = __shfl_down_sync(FULL, st.w[0], 1, LPP);
+            if (sub == LPP - 1) t = fresh;
+#pragma unroll
+            for (int k = 0; k < DPL - 1; ++k) st.w[k] = st.w[k + 1];
+            st.w[DPL - 1] = t;
+        }
+    } else if (FWD) {
+        const int last = (2 * DPL - 1 - ROT) % DPL;     // register of logical element DPL-1 at time ROT == of element 0 at ROT+1
+        DT t = __shfl_up_sync(FULL, st.w[last], 1, LPP);
         if (sub == 0) t = fresh;
-#pragma unroll
-        for (int k = DPL - 1; k > 0; --k) st.w[k] = st.w[k - 1];
-        st.w[0] = t;
+        st.w[last] = t;
+        base = last;
     } else {
-        DT t = __shfl_down_sync(FULL, st.w[0], 1, LPP);
+        const int first = ROT % DPL;                    // register of logical element 0 at time ROT == of element DPL-1 at ROT+1
+        DT t = __shfl_down_sync(FULL, st.w[first], 1, LPP);
         if (sub == LPP - 1) t = fresh;
-#pragma unroll
-        for (int k = 0; k < DPL - 1; ++k) st.w[k] = st.w[k + 1];
-        st.w[DPL - 1] = t;
+        st.w[first] = t;
+        base = (first + 1) % DPL;
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        uint32_t c0 = desc_popc(cl ^ st.w[2 * r]);
-        uint32_t c1 = desc_popc(cl ^ st.w[2 * r + 1]);
+        uint32_t c0 = desc_popc(cl ^ st.w[(base + 2 * r) % DPL]);
+        uint32_t c1 = desc_popc(cl ^ st.w[(base + 2 * r + 1) % DPL]);
         if (BORDER) {                                   // right column x - d < 0  ->  cost 127 (SemiGlobalMatching.c:170-172)
             c0 = (dbase + 2 * r <= x) ? c0 : 127u;
             c1 = (dbase + 2 * r + 1 <= x) ? c1 : 127u;
         }
-        st.C[r] = c1 * 65536u + c0;
+        st.C[r] = __byte_perm(c0, c1, 0x5410);
     }
     int dg = (int)g - (int)st.g;
     dg = dg < 0 ? -dg : dg;
@@ -247,15 +269,15 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
 }
 
 // n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
-// prepares the following step from lane i of the group (when `more`).
-template <int NR, int LPP, bool FWD, bool BORDER, typename DT>
+// prepares the following step from lane i of the group.  WRAP: see dp_step.
+template <int NR, int LPP, bool FWD, bool BORDER, bool WRAP, typename DT>
 __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD, DT>& st, const uint32_t (&padm)[NR], int n,
                                                  int xnext, uint32_t gBlk, DT clBlk, DT crBlk, int sub, int dbase,
                                                  uint8_t*& out, long long outStride, bool stores)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    for (int i = 0; i < n; ++i) {
-        // ---- dependent chain of the current step
+    constexpr int DPL = 2 * NR;
+    auto chain = [&]() {                                // dependent chain of the current step
         uint32_t Ccur[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) Ccur[r] = st.C[r];
@@ -264,12 +286,30 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
         uint32_t dn = __shfl_down_sync(FULL, st.L[0], 1, LPP);
         if (sub == 0) up = 0x00FF00FFu;
         if (sub == LPP - 1) dn = 0x00FF00FFu;
-        dp_step<NR>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
+        dp_step<NR, WRAP>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
         st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
         if (stores) store_plane<NR>(out, st.L);
         out += outStride;
-        // ---- inputs of the next step (independent of the chain above)
-        horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase);
+    };
+    if (DPL <= 8) {
+        // chunks of DPL steps, fully unrolled: the window rotates through its registers without moves.  Only the last
+        // block of a row can end inside a chunk (n < LPP), and nothing reads the window after it, so leaving the
+        // chunk early there is harmless.  (Windows of 16 descriptors, D = 256: unrolling 16 steps costs more in
+        // registers and code size than the moves it saves.)
+        for (int i = 0; i < n; i += DPL) {
+#pragma unroll
+            for (int t = 0; t < DPL; ++t) {
+                if (i + t >= n) break;
+                chain();
+                // inputs of the next step (independent of the chain above)
+                horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i + t, FWD ? xnext + i + t : xnext - i - t, sub, dbase, t);
+            }
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            chain();
+            horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase, -1);
+        }
     }
 }
 
@@ -292,7 +332,8 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     }
     const int dbase = P.dmin + DPL * sub;
     const int dlast = P.dmin + LPP * DPL - 1;
-    const bool stores = active && (DPL * sub < P.Dp);
+    // without padding every lane holds real disparities; idle groups shadow the last path and store the same bytes again
+    const bool stores = PAD ? (active && (DPL * sub < P.Dp)) : true;
     const long long outStride = FWD ? (long long)P.Dp : -(long long)P.Dp;
     uint8_t* out = P.planes + (size_t)job.dir * P.planeStride + ((size_t)rowBase + (FWD ? 0 : W - 1)) * P.Dp + DPL * sub;
 
@@ -336,7 +377,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     }
     if (W == 1) return;
     // prepare step 1 from lane 0 of block 0; afterwards every block iteration consumes one step and prepares the next
-    horizontal_prepare<NR, LPP, FWD, true, DT>(P, st, gA, clA, crA, 0, column(1), sub, dbase);
+    horizontal_prepare<NR, LPP, FWD, true, DT>(P, st, gA, clA, crA, 0, column(1), sub, dbase, -1);
     // steps 1 .. W-1: step s is consumed in block (s-1)/LPP at i = (s-1)%LPP, where step s+1 is prepared from lane i+1
     // of the same block, or lane 0 of the next one.  To keep one loop body, rotate the block registers by one lane:
     // consuming position i prepares from lane i of registers that hold steps LPP*b+2 .. LPP*b+LPP+1.
@@ -347,6 +388,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
         const auto first = __shfl_sync(FULL, nxt, 0, LPP);
         return sub == LPP - 1 ? first : v;
     };
+    bool prevBorder = true;                                          // step 1 was prepared with the border handling
     for (int b = 0; done < nsteps; ++b) {
         load_block(b + 1, gB, clB, crB);                             // one block ahead
         const uint32_t gS = shifted(gA, gB);
@@ -355,8 +397,12 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
         const int sPrepFirst = done + 2;
         const int xa = column(min(sPrepFirst, W - 1)), xb = column(min(sPrepFirst + n - 1, W - 1));
         const bool border = min(xa, xb) < dlast;                     // warp-uniform
-        if (border) horizontal_block<NR, LPP, FWD, true, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
-        else        horizontal_block<NR, LPP, FWD, false, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        // the first step a block consumes was prepared by the previous block: no truncation only if neither saw the border
+        // (two code variants only: the border one is also correct, just slower, for interior columns)
+        const bool slow = border || prevBorder || P.wrapInterior != 0;
+        if (slow) horizontal_block<NR, LPP, FWD, true, true, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        else      horizontal_block<NR, LPP, FWD, false, false, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        prevBorder = border;
         done += n;
         gA = gB; clA = clB; crA = crB;
     }
@@ -393,7 +439,8 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
     }
     const int dbase = P.dmin + DPL * sub;                 // absolute disparity of this lane's first index
     const int dlast = P.dmin + DPL * LPP - 1;             // largest absolute disparity the group may hold
-    const bool stores = active && (DPL * sub < P.Dp);
+    // without padding every lane holds real disparities; idle groups shadow the last path and store the same bytes again
+    const bool stores = PAD ? (active && (DPL * sub < P.Dp)) : true;
     uint8_t* const planeLane = P.planes + (size_t)job.dir * P.planeStride + DPL * sub;
     const uint32_t p1x2 = P.p1x2;
     // vertical paths keep their column: whether the left image border matters is decided once per warp
@@ -416,7 +463,9 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
         else pack_cost<NR, false, DT>(in, 0, C);
     };
     auto visit = [&](const StepInput<NR, DT>& in, uint32_t p, int tc) {
-        cost(in, tc);
+        const bool slow = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
+        if (slow) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
+        else pack_cost<NR, false, DT>(in, 0, C);
         int dg = (int)in.g - (int)gPrev;
         dg = dg < 0 ? -dg : dg;
         gPrev = in.g;
@@ -427,7 +476,8 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
         if (sub == 0) up = 0x00FF00FFu;           // Lp[-1] = 255
         if (sub == LPP - 1) dn = 0x00FF00FFu;     // Lp[DPL*LPP] = 255
         if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);   // emit the previous visit before overwriting L
-        dp_step<NR>(L, C, padm, up, dn, p1x2, p2x2, negmin);
+        // (always with the uint8 truncation: a second copy of the step without it, selected per visit, measured 9 % slower)
+        dp_step<NR, true>(L, C, padm, up, dn, p1x2, p2x2, negmin);
         minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
         posPrev = p;
     };
@@ -448,17 +498,25 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
     gPrev = in0.g;
     posPrev = q0;
 
-    int s = 1;      // next visit to process; its inputs are in buffer s % 3, visits s+1 and s+2 are in flight
-    while (s < len) {
-        if (s + 2 < len) { advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0); }
+    int s = 1;      // next visit to process: its inputs are in in1, those of visit s+1 in in2
+    // main loop: three visits per iteration with the buffers rotating statically (no register moves) and every
+    // prefetch unconditional: the last one fetches visit s+4 <= len-1
+    for (; s + 5 <= len; s += 3) {
+        advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0);
         visit(in1, q1, t1);
-        if (++s >= len) break;
-        if (s + 2 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1); }
+        advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1);
         visit(in2, q2, t2);
-        if (++s >= len) break;
-        if (s + 2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2); }
+        advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2);
         visit(in0, q0, t0);
+    }
+    // tail: at most four visits, one at a time
+    while (s < len) {
+        const bool more = s + 2 < len;
+        if (more) { advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0); }
+        visit(in1, q1, t1);
         ++s;
+        in1 = in2; q1 = q2; t1 = t2;
+        if (more) { in2 = in0; q2 = q0; t2 = t0; }
     }
     if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);
 }

@@ -451,6 +451,11 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.planes = s.planes; p.planeStride = c->planeStride; p.side = reinterpret_cast<uint32_t*>(s.side);
         p.entryOf = c->entryOf; p.work = c->work; p.nIrregularWarps = c->nIrregularWarps; p.nRegularWarps = c->nRegularWarps;
         p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity; p.p1x2 = c->p1x2;
+        {   // largest in-image census cost (5x5: 25 bits, 9x7: 63 with the centre bit always equal) + largest penalty
+            const int maxCost = c->descBytes == 8 ? 62 : 25;
+            const int maxP2 = std::min(256, std::max((int)c->opt.p1, (int)c->opt.p2_init));
+            p.wrapInterior = (maxCost + maxP2 > 255) ? 1 : 0;
+        }
         memcpy(p.p2x2, c->p2x2, sizeof p.p2x2);
         const int warps = c->nIrregularWarps + c->nRegularWarps;
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
