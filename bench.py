@@ -241,6 +241,25 @@ def main() -> int:
             barrier()
             batched = {"frames_in_flight": args.inflight, "frames": n, "value": world * n * de_per_frame / (bms * 1e-3) / 1e6,
                        "unit": "MDE/s", "frames_per_s": world * n / (bms * 1e-3)}
+    # ---- extra: config C4's shape (batch of KITTI-shaped pairs, 4 paths), this rank's shard, device-resident
+    batched_c4 = None
+    if args.inflight > 1:
+        opt4 = sgm.default_option(max_disparity=D, num_paths=4, is_remove_speckles=True)
+        with sgm.Context(device=local_rank, slots=args.inflight) as bctx:
+            bctx.set_pipeline(sgm.PIPE_HOTPATH)
+            bctx.configure(W, H, opt4)
+            n = args.inflight * max(2, args.steps // args.inflight)
+            outs = [torch.empty((H, W), dtype=torch.float32, device="cuda") for _ in range(args.inflight)]
+            ls = [d_left.data_ptr()] * n; rs = [d_right.data_ptr()] * n
+            os_ = [outs[k % args.inflight].data_ptr() for k in range(n)]
+            bctx.match_batch_ptrs(ls[:args.inflight], rs[:args.inflight], os_[:args.inflight], device_memory=True)
+            barrier()
+            bctx.match_batch_ptrs(ls, rs, os_, device_memory=True)
+            bms = max_over_ranks(bctx.last_device_ms())
+            barrier()
+            batched_c4 = {"workload": "C4 shape: KITTI-shaped pairs, D=128, 4 paths, contiguous shard per GPU", "frames_in_flight": args.inflight,
+                          "frames": world * n, "value": world * n * de_per_frame / (bms * 1e-3) / 1e6, "unit": "MDE/s",
+                          "frames_per_s": world * n / (bms * 1e-3)}
     # ---- extra: the same workload with the 9x7 / 64-bit census extension (the window BASELINE.json's config text names;
     #      no reference implementation exists for it, so the headline stays on the reference's 5x5 census)
     census97 = None
@@ -304,6 +323,7 @@ def main() -> int:
             "gpu_launches": gpu_launches,
             "gpu_launches_note": f"{launches_per_frame} kernels per hot-path frame in the `value` region; SGM_Match launches {gctx_launches} per frame",
             "batched": batched,
+            "batched_c4": batched_c4,
             "census9x7": census97,
             "clocks": clocks,
         }

@@ -33,7 +33,7 @@ def _worker(rank, w, h, d, paths, span, kind, nsteps, barrier, out_q):
     from soc_project_stereo_matching_b200.synth import make_pair
 
     opts = pyoracle.options(max_disparity=d, num_paths=paths, remove_speckles=True)
-    left, right, _ = make_pair(w, h, d, seed=0xB200 + rank, texture="scene")
+    left, right, _ = make_pair(w, h, d, seed=0xB200 + rank, texture="noise")   # the same inputs as bench.py's GPU arm
     if kind == "reference":
         eng = pyoracle.Reference(w, h, d, "p4" if paths == 4 else "")
         run = (lambda: eng.hotpath(left, right, opts)) if span == "hot" else (lambda: eng.match_plain(left, right, opts))
