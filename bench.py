@@ -146,7 +146,18 @@ def main() -> int:
         raise SystemExit("bench.py: no CUDA device; the SGM library has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator is created; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -194,7 +205,7 @@ def main() -> int:
     wall_ms = (time.perf_counter() - t0) * 1e3
     total_ms = max_over_ranks(total_ms)
     value = world * args.steps * de_per_frame / (total_ms * 1e-3) / 1e6
-    gpu_launches = args.steps * launches_per_frame
+    gpu_launches = world * args.steps * launches_per_frame          # all ranks
     # per-frame latency with a host sync after every frame (what a latency-bound caller sees), L2 flushed in between
     lat_ms, _ = ctx.time_device(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), 3, min(args.steps, 50), True)
 

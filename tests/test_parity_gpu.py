@@ -198,6 +198,26 @@ def test_multi_gpu_batch_entry_point(oracle):
         assert_same(f"multi-gpu[{k}]", got[k], oracle.match(lefts[k], rights[k], opts)["disp_final"])
 
 
+def test_c4_shape_batch_sharded_over_all_devices(oracle):
+    """Config C4's shape at reduced count: a batch of KITTI-shaped pairs, D=128, 4 paths, through
+    SGMB_MatchBatchMultiGPU over every visible device.  Every pair must equal the single-frame result of the same
+    library (shards and slots do not interact) and two of them are checked against the oracle bit for bit."""
+    w, h, d, n = 1242, 375, 128, 12
+    opts = options(max_disparity=d, num_paths=4)
+    opt = to_sgm_option(opts)
+    pairs = [make_pair(w, h, d, seed=0xB200 + k, texture="scene" if k % 3 == 0 else "noise")[:2] for k in range(n)]
+    lefts = np.stack([p[0] for p in pairs]); rights = np.stack([p[1] for p in pairs])
+    ndev = sgm.lib.SGMB_DeviceCount()
+    got = sgm.match_batch_multi_gpu(list(range(ndev)), 3, w, h, opt, sgm.PIPE_HOTPATH, lefts, rights)
+    with sgm.Context(0) as c:
+        c.set_pipeline(sgm.PIPE_HOTPATH)
+        c.configure(w, h, opt)
+        for k in range(n):
+            assert_same(f"C4 batch[{k}] vs single frame", got[k], c.match(lefts[k], rights[k]))
+    for k in (0, n - 1):
+        assert_same(f"C4 batch[{k}] vs oracle", got[k], oracle.hotpath(lefts[k], rights[k], opts))
+
+
 def test_kitti_shape_c2_against_oracle(oracle):
     """Config C2 at full size (1242x375, D=128, 8 paths), both textures: post-LR and final maps bit-exact."""
     w, h, d = 1242, 375, 128
