@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 src = os.path.join(ROOT, "gpurun_out", tag)
 dst = os.path.join(ROOT, "profiles")
-for name in ("bench.json", "bench_reference.json", "launches.csv", "gpu.txt"):
+for name in ("bench.json", "bench_reference.json", "launches.csv", "launches_bench.csv", "gpu.txt"):
     p = os.path.join(src, name)
     if os.path.isfile(p) and os.path.getsize(p):
         shutil.copy(p, os.path.join(dst, f"{tag}_{name}"))

@@ -322,3 +322,25 @@ def test_census_9x7_kitti_shape_and_global_api(oracle):
         assert_same("9x7 C2 disp_lr", got, want["disp_lr"])
         with pytest.raises(sgm.SGMError):
             c.set_census_window(3, 3)
+
+
+def test_random_shapes_and_options_against_oracle(ctx, oracle):
+    """Seeded random sweep over small shapes and every option field (the property-test form of the reference's
+    missing unit tests): all stages bit-exact against the oracle."""
+    rng = np.random.Generator(np.random.PCG64(20261018))
+    for case in range(40):
+        w = int(rng.integers(1, 97)); h = int(rng.integers(1, 49))
+        dmin = int(rng.choice([0, 0, 0, 3, 17]))
+        d = int(rng.choice([1, 2, 7, 16, 31, 48, 64, 65, 100, 128, 129, 200, 256]))
+        p1 = int(rng.choice([0, 1, 10, 40, 300])); p2 = int(p1 + rng.choice([0, 5, 140, 1000]))
+        opts = options(min_disparity=dmin, max_disparity=dmin + d, num_paths=int(rng.choice([4, 8, 8, 1])), p1=p1, p2_init=min(p2, 32767),
+                       check_unique=bool(rng.integers(0, 2)), uniqueness_ratio=float(rng.choice([0.99, 0.95, 0.8])),
+                       check_lr=bool(rng.integers(0, 2)), lrcheck_thres=float(rng.choice([1.0, 0.5, 3.0])),
+                       remove_speckles=bool(rng.integers(0, 2)), min_speckle_area=int(rng.choice([1, 5, 50, 400])))
+        tex = "scene" if rng.integers(0, 2) else "noise"
+        left, right, _ = make_pair(w, h, d, seed=1000 + case, texture=tex)
+        if case % 5 == 0:                                   # flat / saturated images: adaptive P2 at its maximum, ties everywhere
+            left[:] = 255 if case % 10 == 0 else 0
+        want = oracle.match(left, right, opts)
+        got = run_all_stages(ctx, left, right, opts)
+        compare_stages(f"random[{case}] {w}x{h} D={d} dmin={dmin} paths={opts['num_paths']} p1={p1} p2={p2} {tex}", got, want)
