@@ -52,6 +52,8 @@ __device__ __forceinline__ uint32_t desc_popc(desc64_t x) { return (uint32_t)__p
 struct AggParams {
     const uint8_t* img;         // left image [N]
     const void* censusL;        // DT [N]
+    const uint2* pixL;          // 32-bit descriptors only: {left descriptor, grey value} per pixel: what a column visit needs besides
+                                // its right-census window, fetched with ONE vector load (see load_step)
     const void* censusR4;       // DT [16 / sizeof(DT)][copyStride], see census.cuh
     uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
@@ -85,8 +87,24 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
     constexpr int DPL = 2 * NR;
     constexpr int PER16 = 16 / (int)sizeof(DT);           // descriptors per 128-bit load
     constexpr int VEC = DPL < PER16 ? DPL : PER16;        // alignment unit of the window, in descriptors
-    in.g = __ldg(P.img + pos);
-    in.cl = __ldg(static_cast<const DT*>(P.censusL) + pos);
+    if constexpr (sizeof(DT) == 4) {
+        // One 64-bit load instead of two scalar ones.  With scalar loads ptxas let the load overwrite its own address
+        // register and parked the value with a register move a few instructions later - a full L2 latency on the
+        // in-order issue stream (two such moves carried 17 % of the kernel's stall samples, ncu source view of round
+        // r1_e); a vector destination stays where it is loaded.  What remains (8 % of the samples on the first use of
+        // one of the three buffers) is structural: ptxas tracks all prefetch loads of the loop with ONE hardware
+        // scoreboard - the other five rotate among POPCs, shuffles and table lookups (decoded from the control words)
+        // - so the wait before a buffer's first use also waits for the request issued ~70 instructions earlier for
+        // another buffer.  Measured alternatives, all slower or equal: two buffers with the request right behind the
+        // wait (0.288 ms), reloading a buffer inside its consuming visit three visits ahead (0.284 ms), staging through
+        // shared memory with cp.async (0.409 ms: the L1 data pipe, already the busiest unit, then carries every
+        // window three times); this version: 0.282 ms at C2.
+        const uint2 px = __ldg(P.pixL + pos);
+        in.cl = px.x; in.g = px.y;
+    } else {
+        in.g = __ldg(P.img + pos);
+        in.cl = __ldg(static_cast<const DT*>(P.censusL) + pos);
+    }
     const uint32_t y0 = pos - (uint32_t)(P.dmin + DPL * sub + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
     const uint32_t al = (y0 + (VEC - 1)) & ~(uint32_t)(VEC - 1);
     const DT* src = static_cast<const DT*>(P.censusR4) + ((al - y0) * P.copyStride + al);

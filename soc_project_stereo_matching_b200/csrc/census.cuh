@@ -32,6 +32,7 @@ struct CensusParams {
     uint8_t* grey[2];        // PLANAR only: converted grey images [N]
     uint32_t wR, wG, wB;     // PLANAR only: grey = (wR*R + wG*G + wB*B) >> 8
     void* left;              // DT [N]
+    uint2* pixL;             // optional: {left descriptor, grey value} per pixel of the LEFT image (32-bit descriptors only)
     void* right4;            // DT [K][copyStride]
     size_t copyStride;       // elements per copy (padF + N + padB, multiple of 4)
     int padF;
@@ -93,6 +94,7 @@ sgm_census(CensusParams P)
         const size_t p = (size_t)y * W + x;
         if (which == 0) {
             static_cast<DT*>(P.left)[p] = bits;
+            if (sizeof(DT) == 4 && P.pixL) P.pixL[p] = make_uint2((uint32_t)bits, (uint32_t)tile[ty + RY][tx + o + RX]);
         } else {
 #pragma unroll
             for (int a = 0; a < K; ++a) static_cast<DT*>(P.right4)[a * P.copyStride + P.padF + a + p] = bits;

@@ -56,6 +56,7 @@ struct Slot {
     uint8_t* img[2] = {nullptr, nullptr};
     void* censusL = nullptr;          // descriptors: uint32 (5x5 census) or 64-bit (9x7 census)
     void* censusR4 = nullptr;         // [16 / descBytes][copyStride] shifted copies (census.cuh)
+    uint2* pixL = nullptr;            // {left descriptor, grey} per pixel (32-bit descriptors; aggregate.cuh column paths)
     uint8_t* planes = nullptr;
     uint16_t* side = nullptr;
     uint16_t* S = nullptr;            // taps only
@@ -121,6 +122,7 @@ static void free_slot_buffers(Slot& s)
     cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
+    cudaFree(s.pixL); s.pixL = nullptr;
     cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
     s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr;
@@ -361,6 +363,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.censusL, c->N * (size_t)c->descBytes));
         CU(cudaMalloc(&s.censusR4, nCopies * c->copyStride * (size_t)c->descBytes));
         CU(cudaMemset(s.censusR4, 0, nCopies * c->copyStride * (size_t)c->descBytes));
+        if (c->descBytes == 4) CU(cudaMalloc(&s.pixL, c->N * sizeof(uint2)));
         CU(cudaMalloc(&s.planes, (size_t)c->nDirs * c->planeStride));
         // slots on an irregular path's toroidal diagonal are never written by K2 and must read as 0 in K3
         CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
@@ -432,6 +435,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.img[0] = dL; p.img[1] = dR; p.left = s.censusL; p.right4 = s.censusR4;
         p.copyStride = c->copyStride; p.padF = c->padF; p.W = W; p.H = H;
         p.grey[0] = s.img[0]; p.grey[1] = s.img[1];
+        p.pixL = s.pixL;
         p.wR = (c->greyFormula == SGMB_GREY_STB) ? 77u : 76u; p.wG = 150u; p.wB = 29u;
         dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
         const int threads = kCensusTileW * kCensusTileH / 2;
@@ -447,7 +451,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     }
     {   // K2 aggregation
         AggParams p{};
-        p.img = dL; p.censusL = s.censusL; p.censusR4 = s.censusR4; p.copyStride = (uint32_t)c->copyStride; p.padF = c->padF;
+        p.img = dL; p.censusL = s.censusL; p.pixL = s.pixL; p.censusR4 = s.censusR4; p.copyStride = (uint32_t)c->copyStride; p.padF = c->padF;
         p.planes = s.planes; p.planeStride = c->planeStride; p.side = reinterpret_cast<uint32_t*>(s.side);
         p.entryOf = c->entryOf; p.work = c->work; p.nIrregularWarps = c->nIrregularWarps; p.nRegularWarps = c->nRegularWarps;
         p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity; p.p1x2 = c->p1x2;
