@@ -52,8 +52,9 @@ __device__ __forceinline__ uint32_t desc_popc(desc64_t x) { return (uint32_t)__p
 struct AggParams {
     const uint8_t* img;         // left image [N]
     const void* censusL;        // DT [N]
-    const uint2* pixL;          // 32-bit descriptors only: {left descriptor, grey value} per pixel: what a column visit needs besides
-                                // its right-census window, fetched with ONE vector load (see load_step)
+    const void* pixL;           // {left descriptor, grey value} per pixel - uint2 for 32-bit descriptors, uint4 {lo, hi, grey, 0} for
+                                // 64-bit ones: what a column visit needs besides its right-census window, fetched with ONE vector
+                                // load (see load_step)
     const void* censusR4;       // DT [16 / sizeof(DT)][copyStride], see census.cuh
     uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
@@ -99,11 +100,11 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
         // wait (0.288 ms), reloading a buffer inside its consuming visit three visits ahead (0.284 ms), staging through
         // shared memory with cp.async (0.409 ms: the L1 data pipe, already the busiest unit, then carries every
         // window three times); this version: 0.282 ms at C2.
-        const uint2 px = __ldg(P.pixL + pos);
+        const uint2 px = __ldg(static_cast<const uint2*>(P.pixL) + pos);
         in.cl = px.x; in.g = px.y;
     } else {
-        in.g = __ldg(P.img + pos);
-        in.cl = __ldg(static_cast<const DT*>(P.censusL) + pos);
+        const uint4 px = __ldg(static_cast<const uint4*>(P.pixL) + pos);
+        in.cl = ((desc64_t)px.y << 32) | px.x; in.g = px.z;
     }
     const uint32_t y0 = pos - (uint32_t)(P.dmin + DPL * sub + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
     const uint32_t al = (y0 + (VEC - 1)) & ~(uint32_t)(VEC - 1);

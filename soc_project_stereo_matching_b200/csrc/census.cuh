@@ -32,7 +32,8 @@ struct CensusParams {
     uint8_t* grey[2];        // PLANAR only: converted grey images [N]
     uint32_t wR, wG, wB;     // PLANAR only: grey = (wR*R + wG*G + wB*B) >> 8
     void* left;              // DT [N]
-    uint2* pixL;             // optional: {left descriptor, grey value} per pixel of the LEFT image (32-bit descriptors only)
+    void* pixL;              // {left descriptor, grey value} per pixel of the LEFT image: uint2 (32-bit descriptors) or
+                             // uint4 {lo, hi, grey, 0} (64-bit descriptors)
     void* right4;            // DT [K][copyStride]
     size_t copyStride;       // elements per copy (padF + N + padB, multiple of 4)
     int padF;
@@ -94,7 +95,9 @@ sgm_census(CensusParams P)
         const size_t p = (size_t)y * W + x;
         if (which == 0) {
             static_cast<DT*>(P.left)[p] = bits;
-            if (sizeof(DT) == 4 && P.pixL) P.pixL[p] = make_uint2((uint32_t)bits, (uint32_t)tile[ty + RY][tx + o + RX]);
+            const uint32_t grey = tile[ty + RY][tx + o + RX];
+            if (sizeof(DT) == 4) static_cast<uint2*>(P.pixL)[p] = make_uint2((uint32_t)bits, grey);
+            else static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
         } else {
 #pragma unroll
             for (int a = 0; a < K; ++a) static_cast<DT*>(P.right4)[a * P.copyStride + P.padF + a + p] = bits;

@@ -56,7 +56,7 @@ struct Slot {
     uint8_t* img[2] = {nullptr, nullptr};
     void* censusL = nullptr;          // descriptors: uint32 (5x5 census) or 64-bit (9x7 census)
     void* censusR4 = nullptr;         // [16 / descBytes][copyStride] shifted copies (census.cuh)
-    uint2* pixL = nullptr;            // {left descriptor, grey} per pixel (32-bit descriptors; aggregate.cuh column paths)
+    void* pixL = nullptr;             // {left descriptor, grey} per pixel: uint2 / uint4 for 32- / 64-bit descriptors (aggregate.cuh)
     uint8_t* planes = nullptr;
     uint16_t* side = nullptr;
     uint16_t* S = nullptr;            // taps only
@@ -363,7 +363,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.censusL, c->N * (size_t)c->descBytes));
         CU(cudaMalloc(&s.censusR4, nCopies * c->copyStride * (size_t)c->descBytes));
         CU(cudaMemset(s.censusR4, 0, nCopies * c->copyStride * (size_t)c->descBytes));
-        if (c->descBytes == 4) CU(cudaMalloc(&s.pixL, c->N * sizeof(uint2)));
+        CU(cudaMalloc(&s.pixL, c->N * (c->descBytes == 4 ? sizeof(uint2) : sizeof(uint4))));
         CU(cudaMalloc(&s.planes, (size_t)c->nDirs * c->planeStride));
         // slots on an irregular path's toroidal diagonal are never written by K2 and must read as 0 in K3
         CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
