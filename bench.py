@@ -252,6 +252,25 @@ def main() -> int:
             barrier()
             batched = {"frames_in_flight": args.inflight, "frames": n, "value": world * n * de_per_frame / (bms * 1e-3) / 1e6,
                        "unit": "MDE/s", "frames_per_s": world * n / (bms * 1e-3)}
+    # ---- extra: end to end for a batch through SGMB_MatchBatch (pinned host buffers in and out, full SGM_Match pipeline):
+    #      copies and kernels of different pairs overlap over the context's slots
+    e2e_batched = None
+    if args.inflight > 1:
+        with sgm.Context(device=local_rank, slots=args.inflight) as bctx:
+            bctx.set_pipeline(sgm.PIPE_REFERENCE)
+            bctx.configure(W, H, opt)
+            n = args.inflight * max(2, args.steps // args.inflight)
+            h_outs = [torch.empty((H, W), dtype=torch.float32).pin_memory() for _ in range(n)]
+            ls = [h_left.data_ptr()] * n; rs = [h_right.data_ptr()] * n; os_ = [t.data_ptr() for t in h_outs]
+            bctx.match_batch_ptrs(ls[:args.inflight], rs[:args.inflight], os_[:args.inflight], device_memory=False)
+            barrier()
+            t0 = time.perf_counter()
+            bctx.match_batch_ptrs(ls, rs, os_, device_memory=False)
+            barrier()
+            bs = max_over_ranks(time.perf_counter() - t0)
+            e2e_batched = {"api": "SGMB_MatchBatch, pinned host buffers, hot path + speckle filter + in-place median", "frames_in_flight": args.inflight,
+                           "frames": world * n, "value": world * n * de_per_frame / bs / 1e6, "unit": "MDE/s", "ms_per_frame": bs / n * 1e3,
+                           "h2d_bytes_per_frame": 2 * W * H, "d2h_bytes_per_frame": 4 * W * H}
     # ---- extra: config C4's shape (batch of KITTI-shaped pairs, 4 paths), this rank's shard, device-resident
     batched_c4 = None
     if args.inflight > 1:
@@ -334,6 +353,7 @@ def main() -> int:
             "gpu_launches": gpu_launches,
             "gpu_launches_note": f"{launches_per_frame} kernels per hot-path frame in the `value` region; SGM_Match launches {gctx_launches} per frame",
             "batched": batched,
+            "e2e_batched": e2e_batched,
             "batched_c4": batched_c4,
             "census9x7": census97,
             "clocks": clocks,
