@@ -17,11 +17,13 @@
 // __reduce_min_sync (LPP == 32) or a shuffle butterfly; all path state lives in registers.  Candidates may
 // exceed 255 (they can never win against Lp[d] <= 255); only the final C + m - minPrev is wrapped.
 //
-// The kernel is bound by instruction issue, not by HBM (ncu: profiles/), so the per-step overhead that
-// does not depend on the number of disparities (position update, the three loads, penalty lookup, the two
-// shuffles, the min reduction, the store) is amortised by giving each lane MORE disparities and putting
-// 32/LPP paths of the same direction in one warp.  The horizontal directions have only H paths of W steps
-// each and are the latency-critical ones, so they keep more lanes per path.
+// The kernel is bound by its instruction count times the latency of dependent instructions, not by HBM or by
+// any pipe (ncu: profiles/), so the per-step overhead that does not depend on the
+// number of disparities (position update, the loads, penalty lookup, the two shuffles, the min reduction, the
+// store) is amortised by giving each lane MORE disparities and putting 32/LPP paths of the same direction in
+// one warp.  The horizontal directions have only H paths of W steps each, so they keep more lanes per path.
+// Templates: DT = census descriptor type (uint32_t: the reference's 5x5 census; desc64_t: the 9x7 extension),
+// PAD = whether some lanes hold disparity slots beyond D (false for D = 64 / 128 / 256).
 //
 // Output: each direction r owns a uint8 plane [N][Dp]; a group stores L_r(p, .) with one coalesced store
 // per pixel.  No direction reads or modifies another one's data, so all directions run concurrently in ONE
