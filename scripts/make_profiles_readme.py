@@ -36,6 +36,16 @@ used as bench values.
 """
 if n2:
     txt += f"| 2 GPUs under torchrun (one frame per rank per step, no collective) | {n2['value']/1e3:.1f} GDE/s, {n2['ms_per_step']:.3f} ms per step; C4 shape {n2['batched_c4']['value']/1e3:.1f} GDE/s | `{tag}_bench_n2.json` |\n"
+if os.path.isfile(P(f"{tag}_configs.jsonl")):
+    txt += f"""
+## All BASELINE.json config shapes, device-resident hot path, one frame at a time (`{tag}_configs.jsonl`, `profiles/prof_configs.py`)
+
+| config | ms per frame | GDE/s | K2 ms | fraction of the HBM roofline (algorithmic bytes of SURVEY §8d ÷ time ÷ measured peak) |
+|---|---|---|---|---|
+"""
+    for line in open(P(f"{tag}_configs.jsonl")):
+        c = json.loads(line)
+        txt += f"| {c['config']} | {c['ms_per_frame']:.3f} | {c['MDE_per_s']/1e3:.1f} | {c['aggregation_ms']:.3f} | {c['frame_roofline_frac']:.2f} |\n"
 txt += f"""
 Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}× (the driver computes its own).
 
