@@ -117,3 +117,30 @@ def test_host_side_path_topology_matches_oracle(oracle):
     for r, want in zip(range(4, 8), (0, 1241, 0, 1241)):
         assert list(np.nonzero(sgm.debug_classify_paths(1242, 375, r))[0]) == [want]
     assert not sgm.debug_classify_paths(1242, 375, 0).any() and not sgm.debug_classify_paths(1242, 375, 2).any()
+
+
+def _build_example(tmp):
+    exe = os.path.join(tmp, "frame_loop")
+    libdir = os.path.dirname(lib_build.LIB)
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", f"-I{INCLUDE}", "-o", exe, os.path.join(ROOT, "examples", "frame_loop.c"),
+                    f"-L{libdir}", "-lsgm_b200", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    return exe
+
+
+def test_plain_c_example_compiles_and_links():
+    """examples/frame_loop.c: a C caller using only include/*.h (the reference's call sequence + the frame loop)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = _build_example(tmp)
+        if not gpu_available():
+            res = subprocess.run([exe], capture_output=True, text=True)
+            assert res.returncode != 0 and "SGM_Initialize" in res.stderr      # fails loudly, no CPU fallback
+
+
+@pytest.mark.gpu
+def test_plain_c_example_runs_on_the_gpu():
+    with tempfile.TemporaryDirectory() as tmp:
+        res = subprocess.run([_build_example(tmp)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert "within 0.5 px of the true shift 9" in res.stdout and "reply of" in res.stdout
+        valid, total, close = (int(x) for x in re.findall(r"(\d+) of (\d+) pixels valid, (\d+) within", res.stdout)[0])
+        assert valid > 0.5 * total and close > 0.99 * valid
