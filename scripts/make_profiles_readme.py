@@ -6,14 +6,16 @@ tag = sys.argv[1]
 P = lambda n: os.path.join(ROOT, "profiles", n)
 j = json.load(open(P(f"{tag}_bench.json"))); r = json.load(open(P(f"{tag}_bench_reference.json"))); t = json.load(open(P("traffic.json")))
 n2 = None
-if os.path.isfile(P(f"{tag}_bench_n2.json")):
-    n2 = json.load(open(P(f"{tag}_bench_n2.json")))
+n2file = next((f for f in (f"{tag}_bench_n2.json", "r1_e_bench_n2.json") if os.path.isfile(P(f))), None)
+if n2file:
+    n2 = json.load(open(P(n2file)))
+n2path = None
 hist = [("r1_a (first CUDA path)", "65.6 GDE/s", "0.909", "0.652 ms", "—"),
         ("r1_c (session 2)", "123.5 GDE/s", "0.483", "0.336 ms", "69.1 GDE/s (0.863 ms)"),
         ("r1_e (session 3, mid)", "136.5 GDE/s", "0.437", "0.290 ms", "73.1 GDE/s (0.815 ms)")]
 txt = f"""# profiles/ — measured numbers and ncu evidence (round 1)
 
-Every file is named per capture: `r1_a` (first CUDA path), `r1_c` (end of session 2), `r1_e` / `r1_f` (session 3; `{tag}` is current).
+Every file is named per capture: `r1_a` (first CUDA path), `r1_c` (end of session 2), `r1_e` / `{tag}` (session 3; `{tag}` is current).
 All runs: one NVIDIA B200 (148 SMs, SM clock 1965 MHz during the timed regions, no throttle reason), image of this
 repository, `scripts/gpu_round.sh <tag>` = smoke → `pytest -m gpu` → `bench.py` → `bench.py --impl reference` →
 ncu launch lists (`--metrics gpu__time_duration.sum --clock-control none`; `{tag}_launches_bench.csv` is the list of the
@@ -35,7 +37,7 @@ used as bench values.
 | `cpu_baseline` inside the GPU arm's line (same code, hot-path span only) | {j['cpu_baseline']['value']:.0f} MDE/s on {j['cpu_baseline']['cores']} cores | `{tag}_bench.json` |
 """
 if n2:
-    txt += f"| 2 GPUs under torchrun (one frame per rank per step, no collective) | {n2['value']/1e3:.1f} GDE/s, {n2['ms_per_step']:.3f} ms per step; C4 shape {n2['batched_c4']['value']/1e3:.1f} GDE/s | `{tag}_bench_n2.json` |\n"
+    txt += f"| 2 GPUs under torchrun (one frame per rank per step, no collective) | {n2['value']/1e3:.1f} GDE/s, {n2['ms_per_step']:.3f} ms per step; C4 shape {n2['batched_c4']['value']/1e3:.1f} GDE/s | `{n2file}` |\n"
 if os.path.isfile(P(f"{tag}_configs.jsonl")):
     txt += f"""
 ## All BASELINE.json config shapes, device-resident hot path, one frame at a time (`{tag}_configs.jsonl`, `profiles/prof_configs.py`)
