@@ -48,6 +48,17 @@ if os.path.isfile(P(f"{tag}_configs.jsonl")):
     for line in open(P(f"{tag}_configs.jsonl")):
         c = json.loads(line)
         txt += f"| {c['config']} | {c['ms_per_frame']:.3f} | {c['MDE_per_s']/1e3:.1f} | {c['aggregation_ms']:.3f} | {c['frame_roofline_frac']:.2f} |\n"
+scal = [(1, j)] + [(n, json.load(open(P(f"{tag}_bench_n{n}.json")))) for n in (2, 4, 8) if os.path.isfile(P(f"{tag}_bench_n{n}.json"))]
+if len(scal) > 1:
+    txt += f"""
+## Scaling over the GPUs of one box (`bench.py` under torchrun, weak scaling: one frame per rank per step, no data-path collective)
+
+| GPUs | `value` GDE/s | ms per step | vs N×(1 GPU) | `e2e` GDE/s | C4 shape batched GDE/s (frames/s) | file |
+|---|---|---|---|---|---|---|
+"""
+    for n, b in scal:
+        txt += (f"| {n} | {b['value']/1e3:.1f} | {b['ms_per_step']:.3f} | {b['value']/(n*j['value']):.3f} | {b['e2e']['value']/1e3:.1f} | "
+                f"{b['batched_c4']['value']/1e3:.1f} ({b['batched_c4']['frames_per_s']:.0f}) | `{tag}_bench{'' if n == 1 else '_n%d' % n}.json` |\n")
 txt += f"""
 Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}× (the driver computes its own).
 
