@@ -162,9 +162,12 @@ float  SGMB_LastDeviceMs(SGMB_Context* ctx);
 int SGMB_TimeDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int warmup,
                     int iters, int flush_l2, float* frame_ms, float* aggr_kernel_ms);
 
-/* Enqueue `iters` device-resident frames back to back on slot 0 without host synchronisation and time the
- * whole region with CUDA events on that stream (*total_ms); agg_ms (optional, [iters]) receives the duration
- * of every aggregation-kernel launch inside the region. */
+/* Run `iters` device-resident frames back to back on slot 0 without host synchronisation and time the whole region
+ * with CUDA events on that stream (*total_ms); agg_ms (optional, [iters]) receives the duration of every
+ * aggregation-kernel launch inside the region.  The frames are recorded into one CUDA graph (kernels, the side-buffer
+ * memset, external event records for agg_ms) and replayed with a single launch; pipelines that include the in-place
+ * median, whose exchange epoch changes per frame, are enqueued kernel by kernel instead (as is everything when the
+ * environment variable SGM_B200_NO_GRAPH is set). */
 int SGMB_RunDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int iters,
                    float* total_ms, float* agg_ms);
 

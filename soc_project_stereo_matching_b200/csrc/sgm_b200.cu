@@ -109,6 +109,7 @@ struct SGMB_Context {
     size_t flushBytes = 0;
     float lastMs = 0.f;
     bool tapsAllocated = false;
+    bool capturing = false;       // enqueue_frame is being recorded into a CUDA graph (SGMB_RunDevice)
 };
 
 static int ensure_device(SGMB_Context* c)
@@ -464,7 +465,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         const int warps = c->nIrregularWarps + c->nRegularWarps;
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
         const int threads = kAggWarpsPerBlock * 32;
-        if (timeAgg) CU(cudaEventRecord(s.evAgg0, s.stream));
+        if (timeAgg) CU(cudaEventRecordWithFlags(s.evAgg0, s.stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         // PAD = false when the disparity range fills every lane of every layout exactly (see aggregate.cuh)
         const bool pad = (D != 64 * c->NR) || (c->altLayout == 2);
 #define SGM_AGG_LAUNCH(NRH, LPPH, NRV, LPPV, NRI, DT)                                                          \
@@ -483,7 +484,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
             else                 SGM_AGG_LAUNCH(8, 16, 8, 16, 4, desc64_t);
         }
 #undef SGM_AGG_LAUNCH
-        if (timeAgg) CU(cudaEventRecord(s.evAgg1, s.stream));
+        if (timeAgg) CU(cudaEventRecordWithFlags(s.evAgg1, s.stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ++nk;
     }
     float* lrOut = s.dispLR;
@@ -951,13 +952,41 @@ extern "C" int SGMB_RunDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t*
         for (auto& e : ev) CU(cudaEventCreate(&e));
     }
     cudaEvent_t keep0 = s.evAgg0, keep1 = s.evAgg1;
-    CU(cudaEventRecord(s.evStart, s.stream));
+    // The frames are recorded into ONE CUDA graph (kernel nodes, the side-buffer memset and - when asked for - external
+    // event records around every aggregation kernel) and replayed with a single launch: the launch-bound inner loop of
+    // a device-resident batch.  Pipelines with the in-place median are enqueued directly (its exchange epoch is a kernel
+    // argument that changes every frame).
+    const bool useGraph = !(c->pipeline & SGMB_PIPE_MEDIAN) && !getenv("SGM_B200_NO_GRAPH");
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
     int rc = SGMB_OK;
+    if (useGraph) {
+        CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+    } else {
+        CU(cudaEventRecord(s.evStart, s.stream));
+    }
     for (int it = 0; it < iters && rc == SGMB_OK; ++it) {
         if (agg_ms) { s.evAgg0 = ev[2 * it]; s.evAgg1 = ev[2 * it + 1]; }
         rc = enqueue_frame(c, s, dL, dR, dOut, agg_ms != nullptr, nullptr);
     }
     s.evAgg0 = keep0; s.evAgg1 = keep1;
+    if (useGraph) {
+        c->capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        if (rc == SGMB_OK && e != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        if (rc == SGMB_OK) {
+            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+            if (e2 != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+        }
+        if (rc == SGMB_OK) {
+            cudaGraphUpload(exec, s.stream);
+            cudaStreamSynchronize(s.stream);
+            cudaEventRecord(s.evStart, s.stream);
+            const cudaError_t e3 = cudaGraphLaunch(exec, s.stream);
+            if (e3 != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e3));
+        }
+    }
     if (rc == SGMB_OK) {
         CU(cudaEventRecord(s.evStop, s.stream));
         CU(cudaStreamSynchronize(s.stream));
@@ -965,6 +994,8 @@ extern "C" int SGMB_RunDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t*
         if (total_ms) *total_ms = c->lastMs;
         if (agg_ms) for (int it = 0; it < iters; ++it) CU(cudaEventElapsedTime(&agg_ms[it], ev[2 * it], ev[2 * it + 1]));
     }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
 }
