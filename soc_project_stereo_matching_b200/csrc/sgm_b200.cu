@@ -73,6 +73,9 @@ struct Slot {
     uint8_t* framePlanes = nullptr;   // SGMB_MatchFrame: left B,G,R then right B,G,R planes [6][N] (allocated on first use)
     float* depth = nullptr;           // SGMB_MatchFrame with calibration: depth map [N] (allocated on first use)
     unsigned medianEpoch = 0;
+    // SGMB_Match / SGMB_MatchBatch always run the frame on the slot's own image buffers, so the whole frame (memsets and
+    // kernels) is recorded once into a CUDA graph and replayed by every later call until the configuration changes
+    cudaGraphExec_t frameExec = nullptr;
     bool busy = false;
 };
 
@@ -118,8 +121,14 @@ static int ensure_device(SGMB_Context* c)
     return SGMB_OK;
 }
 
+static void drop_frame_graph(Slot& s)
+{
+    if (s.frameExec) { cudaGraphExecDestroy(s.frameExec); s.frameExec = nullptr; }
+}
+
 static void free_slot_buffers(Slot& s)
 {
+    drop_frame_graph(s);
     cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
@@ -408,6 +417,7 @@ extern "C" int SGMB_SetCensusWindow(SGMB_Context* c, int width, int height)
 extern "C" int SGMB_SetPipeline(SGMB_Context* c, unsigned flags)
 {
     if (!c) return fail(SGMB_E_ARG, "NULL context");
+    if (flags != c->pipeline) for (auto& s : c->slots) drop_frame_graph(s);
     c->pipeline = flags;
     if (c->configured && (flags & SGMB_PIPE_TAPS)) {
         if (int rc = ensure_device(c)) return rc;
@@ -430,6 +440,12 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     int nk = 0;
 
     if (c->nEntries > 0) CU(cudaMemsetAsync(s.side, 0, (size_t)c->nEntries * c->Dp * sizeof(uint16_t), s.stream));
+    if (doMedian) {
+        // the wavefront's exchange rows are cleared every frame (a few hundred KB, long before they are used), so the tag
+        // epoch can stay constant and the frame has no per-launch kernel argument: it can be replayed as a CUDA graph
+        CU(cudaMemsetAsync(s.xchg, 0, (size_t)((H + 31) / 32) * W * sizeof(unsigned long long), s.stream));
+        s.medianEpoch = 0;
+    }
 
     {   // K1 census
         CensusParams p{};
@@ -541,6 +557,30 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     return SGMB_OK;
 }
 
+// The frame on the slot's own image buffers: recorded into a graph on first use, replayed afterwards.
+static int launch_slot_frame(SGMB_Context* c, Slot& s)
+{
+    static const bool noGraph = getenv("SGM_B200_NO_GRAPH") != nullptr;
+    if (noGraph) return enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr);
+    if (!s.frameExec) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+        int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr);
+        c->capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        if (rc == SGMB_OK && e != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        if (rc == SGMB_OK) {
+            const cudaError_t e2 = cudaGraphInstantiate(&s.frameExec, graph, 0);
+            if (e2 != cudaSuccess) { s.frameExec = nullptr; rc = fail(SGMB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc) return rc;
+    }
+    CU(cudaGraphLaunch(s.frameExec, s.stream));
+    return SGMB_OK;
+}
+
 static float* frame_result(SGMB_Context* c, Slot& s)
 {
     const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
@@ -557,7 +597,7 @@ extern "C" int SGMB_Match(SGMB_Context* c, const uint8_t* L, const uint8_t* R, f
     CU(cudaEventRecord(s.evStart, s.stream));
     CU(cudaMemcpyAsync(s.img[0], L, c->N, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.img[1], R, c->N, cudaMemcpyHostToDevice, s.stream));
-    if (int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr)) return rc;
+    if (int rc = launch_slot_frame(c, s)) return rc;
     if (out) CU(cudaMemcpyAsync(out, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     CU(cudaEventRecord(s.evStop, s.stream));
     CU(cudaStreamSynchronize(s.stream));
@@ -606,7 +646,7 @@ static int run_batch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* c
         } else {
             CU(cudaMemcpyAsync(s.img[0], Ls[k], c->N, cudaMemcpyHostToDevice, s.stream));
             CU(cudaMemcpyAsync(s.img[1], Rs[k], c->N, cudaMemcpyHostToDevice, s.stream));
-            if (int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr)) return rc;
+            if (int rc = launch_slot_frame(c, s)) return rc;
             CU(cudaMemcpyAsync(outs[k], frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         }
     }
