@@ -6,7 +6,15 @@ tag = sys.argv[1]
 P = lambda n: os.path.join(ROOT, "profiles", n)
 j = json.load(open(P(f"{tag}_bench.json"))); r = json.load(open(P(f"{tag}_bench_reference.json"))); t = json.load(open(P("traffic.json")))
 n2 = None
-n2file = next((f for f in (f"{tag}_bench_n2.json", "r1_e_bench_n2.json") if os.path.isfile(P(f))), None)
+import glob
+def multi(n):
+    """Bench line of an N-GPU run: this capture's if present, else the latest earlier one."""
+    own = P(f"{tag}_bench_n{n}.json")
+    if os.path.isfile(own):
+        return os.path.basename(own)
+    older = sorted(glob.glob(P(f"r1_?_bench_n{n}.json")))
+    return os.path.basename(older[-1]) if older else None
+n2file = multi(2)
 if n2file:
     n2 = json.load(open(P(n2file)))
 n2path = None
@@ -48,7 +56,7 @@ if os.path.isfile(P(f"{tag}_configs.jsonl")):
     for line in open(P(f"{tag}_configs.jsonl")):
         c = json.loads(line)
         txt += f"| {c['config']} | {c['ms_per_frame']:.3f} | {c['MDE_per_s']/1e3:.1f} | {c['aggregation_ms']:.3f} | {c['frame_roofline_frac']:.2f} |\n"
-scal = [(1, j)] + [(n, json.load(open(P(f"{tag}_bench_n{n}.json")))) for n in (2, 4, 8) if os.path.isfile(P(f"{tag}_bench_n{n}.json"))]
+scal = [(1, j, f"{tag}_bench.json")] + [(n, json.load(open(P(multi(n)))), multi(n)) for n in (2, 4, 8) if multi(n)]
 if len(scal) > 1:
     txt += f"""
 ## Scaling over the GPUs of one box (`bench.py` under torchrun, weak scaling: one frame per rank per step, no data-path collective)
@@ -56,9 +64,10 @@ if len(scal) > 1:
 | GPUs | `value` GDE/s | ms per step | vs N×(1 GPU) | `e2e` GDE/s | C4 shape batched GDE/s (frames/s) | file |
 |---|---|---|---|---|---|---|
 """
-    for n, b in scal:
+    for n, b, fn in scal:
         txt += (f"| {n} | {b['value']/1e3:.1f} | {b['ms_per_step']:.3f} | {b['value']/(n*j['value']):.3f} | {b['e2e']['value']/1e3:.1f} | "
-                f"{b['batched_c4']['value']/1e3:.1f} ({b['batched_c4']['frames_per_s']:.0f}) | `{tag}_bench{'' if n == 1 else '_n%d' % n}.json` |\n")
+                f"{b['batched_c4']['value']/1e3:.1f} ({b['batched_c4']['frames_per_s']:.0f}) | `{fn}` |\n")
+    txt += "\n(N > 1 lines named `r1_g_*` were taken one commit before the CUDA-graph replay of the timed region; their N = 1 counterpart was 137.3 GDE/s.)\n"
 txt += f"""
 Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}× (the driver computes its own).
 
