@@ -8,13 +8,14 @@
 //
 // The kernel streams 8 (or 4) byte planes once and is meant to run at HBM speed, so the loads of the NEXT tile
 // (128 bytes per thread, straight into the registers phase A has just consumed) are in flight during phase B.
-// One CTA owns one image row and walks it left to right in tiles of TW columns:
+// One CTA owns one image row and walks it from right to left in tiles of TW columns:
 //   phase A : CPP lanes share a pixel, each owning 16 consecutive disparities (one 128-bit load per plane): add
 //             the planes as packed 16-bit fields (+ the side buffer of irregular paths) and store S into a
 //             shared-memory ring of 2*TW + D columns;
 //   phase B : (after one __syncthreads) half of the CTA scans the LEFT view of the tile's columns, the other half
-//             the RIGHT view of the columns that became complete with this tile (the right view reads the ring
-//             along the diagonal S[x + d][d], SemiGlobalMatching.c:397-399).  Four lanes share a pixel; keys
+//             the RIGHT view of the same number of pixels, those whose first column lies in this tile (the right view
+//             reads the ring along the diagonal S[x + d][d], SemiGlobalMatching.c:397-399; walking right to left, all
+//             later columns of such a pixel are already in the ring).  Four lanes share a pixel; keys
 //             (cost << 16 | d) make "lowest d wins ties" and "second = min over d != best" one integer min / max
 //             each (:390-393,412-419); the four partial results are combined with xor shuffles and parked,
 //             together with the two costs next to the best one, in a 16-byte record per pixel;
@@ -149,12 +150,16 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
         }
     };
 
-    int rightDone = 0;                            // right pixels [0, rightDone) are finished
-    int slotTile = 0;                             // c0 % RB
-    load_tile(0, cur, eCur);
-    for (int c0 = 0; c0 < W; c0 += TW) {
+    // The row is walked from its RIGHT end to the left: a right-view pixel x needs the columns x + dmin .. x + dmin + D - 1,
+    // so with this order it is complete as soon as its own tile has been summed - every tile finishes TW left-view and TW
+    // right-view pixels, and both halves of the CTA have the same amount of work in every tile (walking left to right made
+    // half of the warps idle for the first D columns and left them five tiles' worth of pixels after the last one).
+    const int lastStart = ((W - 1) / TW) * TW;    // first tile processed = rightmost
+    int slotTile = lastStart % RB;                // c0 % RB
+    load_tile(lastStart, cur, eCur);
+    for (int c0 = lastStart; c0 >= 0; c0 -= TW) {
         const int cols = min(TW, W - c0);
-        const bool lastTile = (c0 + TW >= W);
+        const bool firstTile = (c0 == lastStart);
         // ------------------------------------------------------------------ phase A
         const int c = c0 + pix;
         if (c < W && chunkOk) {
@@ -203,7 +208,7 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
             }
         }
         // the loads of the next tile fly during phase B (issued only now: the sums above must not wait on them)
-        if (!lastTile) load_tile(c0 + TW, cur, eCur);
+        if (c0 > 0) load_tile(c0 - TW, cur, eCur);
         __syncthreads();
         // ------------------------------------------------------------------ phase B
         if (!rightRole) {
@@ -230,15 +235,17 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
                 }
             }
         } else if (P.checkLR) {
-            // right pixel x is complete once column x + dmin + D - 1 has been summed (or the row has ended)
-            const int rightEnd = lastTile ? W : max(0, c0 + cols - (P.dmin + D - 1));
-            for (int x0 = rightDone; x0 < rightEnd; x0 += GROUPS) {
+            // right pixels whose first column x + dmin lies in this tile (all their other columns are further right and
+            // already summed); the rightmost tile also takes the pixels without any candidate (x + dmin >= W)
+            const int rightBegin = max(0, c0 - P.dmin);
+            const int rightEnd = firstTile ? W : min(W, c0 + cols - P.dmin);
+            for (int x0 = rightBegin; x0 < rightEnd; x0 += GROUPS) {
                 const int x = x0 + grp;
                 const int first = x + P.dmin;                         // left column of disparity index 0
                 const int n = (x < rightEnd) ? max(0, min(D, W - first)) : 0;
                 WtaPair w{0xFFFFFFFFu, 0xFFFFFFFFu};
-                int slot0 = (first - c0) + slotTile;                  // first % RB (first lies within RB columns of c0)
-                slot0 += (slot0 < 0) ? RB : 0; slot0 += (slot0 < 0) ? RB : 0; slot0 -= (slot0 >= RB) ? RB : 0;
+                int slot0 = slotTile + (first - c0);                  // first % RB; 0 <= first - c0 < TW wherever n > 0
+                slot0 -= (slot0 >= RB) ? RB : 0;
                 {
                     const int kEnd = min(k0 + CH, n);
                     int slot = slot0 + k0; if (slot >= RB) slot -= RB;
@@ -261,9 +268,8 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
                     recR[x] = make_uint4(w.kmin, w.ksec, cost(best - 1) | (cost(best + 1) << 16), 0u);
                 }
             }
-            rightDone = max(rightDone, rightEnd);
         }
-        slotTile += TW; if (slotTile >= RB) slotTile -= RB;
+        slotTile -= TW; if (slotTile < 0) slotTile += RB;
     }
     // ---------------------------------------------------------------------- finish whole pixels from the records
     __syncthreads();
