@@ -105,6 +105,18 @@ int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots_per_device, 
                             const SGMOption* option, unsigned pipeline_flags, const uint8_t* const* lefts,
                             const uint8_t* const* rights, float* const* disps, int n);
 
+/* Persistent variant of the above: one context per device kept alive between batches (no allocation per call).
+ * SGMB_PoolConfigure == SGMB_SetPipeline + SGMB_Configure on every device (one host thread each);
+ * SGMB_PoolMatchBatch shards the pairs like SGMB_MatchBatchMultiGPU and runs SGMB_MatchBatch per device concurrently.
+ * SGMB_PoolContext gives access to a member context (e.g. for SGMB_SetCensusWindow before SGMB_PoolConfigure). */
+typedef struct SGMB_Pool SGMB_Pool;
+int  SGMB_PoolCreate(SGMB_Pool** out, const int* devices, int ndev, int slots_per_device);
+void SGMB_PoolDestroy(SGMB_Pool* pool);
+int  SGMB_PoolSize(SGMB_Pool* pool);
+SGMB_Context* SGMB_PoolContext(SGMB_Pool* pool, int index);
+int  SGMB_PoolConfigure(SGMB_Pool* pool, uint16_t width, uint16_t height, const SGMOption* option, unsigned pipeline_flags);
+int  SGMB_PoolMatchBatch(SGMB_Pool* pool, const uint8_t* const* lefts, const uint8_t* const* rights, float* const* disps, int n);
+
 /* ---- The steps either side of the path in the reference system ---- */
 
 /* Colour -> grey weights used by SGMB_MatchFrame*: grey = (wR*R + 150*G + 29*B) >> 8. */

@@ -85,6 +85,12 @@ def _load() -> C.CDLL:
         "SGMB_MatchBatchDevice": (i32, [vp, vp, vp, vp, i32]),
         "SGMB_MatchBatchMultiGPU": (i32, [vp, i32, i32, u16, u16, C.POINTER(SGMOption), C.c_uint, vp, vp, vp, i32]),
         "SGMB_GetStage": (i32, [vp, i32, vp, C.c_size_t]),
+        "SGMB_PoolCreate": (i32, [C.POINTER(vp), vp, i32, i32]),
+        "SGMB_PoolDestroy": (None, [vp]),
+        "SGMB_PoolSize": (i32, [vp]),
+        "SGMB_PoolContext": (vp, [vp, i32]),
+        "SGMB_PoolConfigure": (i32, [vp, u16, u16, C.POINTER(SGMOption), C.c_uint]),
+        "SGMB_PoolMatchBatch": (i32, [vp, vp, vp, vp, i32]),
         "SGMB_SetGreyFormula": (i32, [vp, i32]),
         "SGMB_MatchFrame": (i32, [vp, vp, vp, vp]),
         "SGMB_MatchFrameDevice": (i32, [vp, vp, vp, vp, i32]),
@@ -360,6 +366,42 @@ def match_batch_multi_gpu(devices, slots_per_device, width, height, option, pipe
     _check(lib.SGMB_MatchBatchMultiGPU(dev, len(devices), slots_per_device, width, height, C.byref(option), pipeline,
                                        pa(l), pa(r), pa(out), n))
     return out
+
+
+class Pool:
+    """Persistent multi-GPU pool: one context per device, batches sharded contiguously (pair k -> device k*ndev//n)."""
+
+    def __init__(self, devices, slots_per_device: int = 2):
+        self._h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        _check(lib.SGMB_PoolCreate(C.byref(self._h), dev, len(devices), slots_per_device))
+        self.width = self.height = 0
+
+    def close(self) -> None:
+        if self._h:
+            lib.SGMB_PoolDestroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self) -> int:
+        return lib.SGMB_PoolSize(self._h)
+
+    def configure(self, width: int, height: int, option: SGMOption, pipeline: int = PIPE_REFERENCE) -> None:
+        _check(lib.SGMB_PoolConfigure(self._h, width, height, C.byref(option), pipeline))
+        self.width, self.height = width, height
+
+    def match_batch(self, lefts: np.ndarray, rights: np.ndarray) -> np.ndarray:
+        l = np.ascontiguousarray(lefts, np.uint8); r = np.ascontiguousarray(rights, np.uint8)
+        n = l.shape[0]
+        out = np.empty((n, self.height, self.width), np.float32)
+        pa = lambda a: (C.c_void_p * n)(*[a[k].ctypes.data for k in range(n)])
+        _check(lib.SGMB_PoolMatchBatch(self._h, pa(l), pa(r), pa(out), n))
+        return out
 
 
 def debug_walk_path(width: int, height: int, direction: int, path: int) -> np.ndarray:

@@ -697,6 +697,82 @@ extern "C" int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots, 
     return SGMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ persistent multi-GPU pool
+// One context per device, kept alive between batches (SGMB_MatchBatchMultiGPU above builds and destroys its contexts on
+// every call, which costs device allocations).  Same sharding rule: pair k of n goes to device k*ndev/n.
+struct SGMB_Pool {
+    std::vector<SGMB_Context*> ctx;
+};
+
+extern "C" int SGMB_PoolCreate(SGMB_Pool** out, const int* devices, int ndev, int slots_per_device)
+{
+    if (!out || !devices || ndev < 1) return fail(SGMB_E_ARG, "SGMB_PoolCreate: bad arguments");
+    *out = nullptr;
+    auto* p = new SGMB_Pool();
+    for (int g = 0; g < ndev; ++g) {
+        SGMB_Context* c = nullptr;
+        const int rc = SGMB_Create(&c, devices[g], slots_per_device);
+        if (rc) { for (auto* x : p->ctx) SGMB_Destroy(x); delete p; return rc; }
+        p->ctx.push_back(c);
+    }
+    *out = p;
+    return SGMB_OK;
+}
+
+extern "C" void SGMB_PoolDestroy(SGMB_Pool* p)
+{
+    if (!p) return;
+    for (auto* c : p->ctx) SGMB_Destroy(c);
+    delete p;
+}
+
+extern "C" int SGMB_PoolSize(SGMB_Pool* p) { return p ? (int)p->ctx.size() : 0; }
+
+extern "C" SGMB_Context* SGMB_PoolContext(SGMB_Pool* p, int index)
+{
+    return (p && index >= 0 && index < (int)p->ctx.size()) ? p->ctx[index] : nullptr;
+}
+
+// Runs fn(context, device index) on one host thread per device and returns the first error.
+template <typename F>
+static int pool_for_each(SGMB_Pool* p, F fn)
+{
+    if (!p) return fail(SGMB_E_ARG, "NULL pool");
+    const int ndev = (int)p->ctx.size();
+    std::vector<int> rcs(ndev, SGMB_OK);
+    std::vector<std::string> msgs(ndev);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ndev; ++g)
+        th.emplace_back([&, g]() {
+            rcs[g] = fn(p->ctx[g], g);
+            if (rcs[g]) msgs[g] = g_err;
+        });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < ndev; ++g)
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", p->ctx[g]->device, msgs[g].c_str());
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_PoolConfigure(SGMB_Pool* p, uint16_t width, uint16_t height, const SGMOption* option, unsigned pipeline_flags)
+{
+    return pool_for_each(p, [&](SGMB_Context* c, int) {
+        int rc = SGMB_SetPipeline(c, pipeline_flags);
+        if (!rc) rc = SGMB_Configure(c, width, height, option);
+        return rc;
+    });
+}
+
+extern "C" int SGMB_PoolMatchBatch(SGMB_Pool* p, const uint8_t* const* lefts, const uint8_t* const* rights, float* const* disps, int n)
+{
+    if (n < 0 || (n > 0 && (!lefts || !rights || !disps))) return fail(SGMB_E_ARG, "SGMB_PoolMatchBatch: bad arguments");
+    if (!p) return fail(SGMB_E_ARG, "NULL pool");
+    const int ndev = (int)p->ctx.size();
+    return pool_for_each(p, [&](SGMB_Context* c, int g) {
+        const int lo = (int)((long long)n * g / ndev), hi = (int)((long long)n * (g + 1) / ndev);   // contiguous shard
+        return hi > lo ? SGMB_MatchBatch(c, lefts + lo, rights + lo, disps + lo, hi - lo) : SGMB_OK;
+    });
+}
+
 // ------------------------------------------------------------------------------------------------ frame formats (N3) and evaluation (N4)
 extern "C" int SGMB_SetGreyFormula(SGMB_Context* c, int formula)
 {

@@ -198,6 +198,25 @@ def test_multi_gpu_batch_entry_point(oracle):
         assert_same(f"multi-gpu[{k}]", got[k], oracle.match(lefts[k], rights[k], opts)["disp_final"])
 
 
+def test_persistent_pool_over_all_devices(oracle):
+    """SGMB_Pool*: contexts kept alive between batches; two batches of different size through the same pool."""
+    w, h, d = 96, 40, 32
+    opts = options(max_disparity=d)
+    ndev = sgm.lib.SGMB_DeviceCount()
+    with sgm.Pool(list(range(ndev)), slots_per_device=2) as pool:
+        assert len(pool) == ndev
+        pool.configure(w, h, to_sgm_option(opts), sgm.PIPE_REFERENCE)
+        for n in (7, 3):
+            pairs = [make_pair(w, h, d, seed=500 + 10 * n + k, texture="scene")[:2] for k in range(n)]
+            lefts = np.stack([p[0] for p in pairs]); rights = np.stack([p[1] for p in pairs])
+            got = pool.match_batch(lefts, rights)
+            for k in range(n):
+                assert_same(f"pool[{n}:{k}]", got[k], oracle.match(lefts[k], rights[k], opts)["disp_final"])
+        pool.configure(w, h, to_sgm_option(opts), sgm.PIPE_HOTPATH)         # re-configuration of a live pool
+        got = pool.match_batch(lefts, rights)
+        assert_same("pool hot path", got[0], oracle.match(lefts[0], rights[0], opts)["disp_lr"])
+
+
 def test_c4_shape_batch_sharded_over_all_devices(oracle):
     """Config C4's shape at reduced count: a batch of KITTI-shaped pairs, D=128, 4 paths, through
     SGMB_MatchBatchMultiGPU over every visible device.  Every pair must equal the single-frame result of the same
