@@ -187,9 +187,12 @@ __global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ 
 //       points to a lower block index, so this cannot deadlock.
 constexpr int kMedianLaunches = 2;
 constexpr int kMedianTileW = 64;      // K5a: columns per block
-constexpr int kMedianBlockSteps = 8;  // K5b: steps per bulk-copy block
-constexpr int kMedianBatch = 4;       // K5b: blocks per exchange batch / super-block (32 steps)
-constexpr int kMedianRing = 8;        // K5b: blocks in the shared-memory ring (bulk copies run kMedianRing - 1 blocks ahead)
+// One bulk copy per 32 steps: the per-block bookkeeping (mbarrier wait, warp syncs, proxy fence, re-arming the copy) costs
+// several hundred cycles of a lone warp, so the block is as long as the exchange batch allows (measured at C2: 4 steps per
+// block 281 us, 8: 216 us, 16: 197 us, 32: 176 us).
+constexpr int kMedianBlockSteps = 32; // K5b: steps per bulk-copy block (20 KB)
+constexpr int kMedianBatch = 1;       // K5b: blocks per exchange batch / super-block (32 steps)
+constexpr int kMedianRing = 2;        // K5b: blocks in the shared-memory ring (the next block's copy runs during the current block)
 constexpr int kMedianFrontPad = 8;    // K5b starts kMedianFrontPad steps early (feeds a, b of the first interior column)
 constexpr int kMedianStepBytes = 5 * 32 * 4;
 
