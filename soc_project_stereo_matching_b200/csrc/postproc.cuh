@@ -320,9 +320,9 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
 }
 
 template <bool HAS_ABOVE>
-__device__ __forceinline__ void median_wavefront_body(const float* __restrict__ prep, float* __restrict__ out, unsigned long long* xchg,
-                                                      int W, int H, unsigned epoch, float (*ring)[kMedianBlockSteps][5][32],
-                                                      unsigned long long* mbar)
+__device__ __forceinline__ void median_wavefront_body(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow,
+                                                      unsigned long long* xchg, int W, int H, unsigned epoch,
+                                                      float (*ring)[kMedianBlockSteps][5][32], unsigned long long* mbar)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BS = kMedianBlockSteps, NB = kMedianBatch, NR = kMedianRing;
@@ -331,9 +331,9 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
     const int lane = threadIdx.x;
     const int g = blockIdx.x;
     const int i = 32 * g + lane;
-    const int Wrow = (i < H) ? W : 0;                                         // idle rows store nothing
+    const int Wrow = W;                                                       // rows beyond the image (last group) run like the others and write to a scratch row
     const bool publishes = (lane == 31) && (32 * (g + 1) < H);                // someone consumes this row
-    float* outRow = out + (size_t)(i < H ? i : 0) * W;
+    float* outRow = (i < H) ? out + (size_t)i * W : scratchRow;
     unsigned long long* myX = xchg + (size_t)g * W;
     const unsigned long long* aboveX = HAS_ABOVE ? xchg + (size_t)(g - 1) * W : nullptr;
     const unsigned tagBase = epoch << 16;
@@ -418,7 +418,7 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
             __syncwarp();
         };
         // all 32 lanes are inside their rows for every step of the super-block <=> s0 >= 62 and s0 + 31 < W (and the row exists)
-        const bool interior = __all_sync(FULL, Wrow > 0) && s0 >= 62 && s0 + NB * BS <= W;
+        const bool interior = s0 >= 62 && s0 + NB * BS <= W;
         if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
         else          median_superblock<HAS_ABOVE, true>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
     }
@@ -429,25 +429,27 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(32)
-median_wavefront(const float* __restrict__ prep, float* __restrict__ out, unsigned long long* xchg, int W, int H, unsigned epoch)
+median_wavefront(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow, unsigned long long* xchg, int W, int H,
+                 unsigned epoch)
 {
     __shared__ __align__(128) float ring[kMedianRing][kMedianBlockSteps][5][32];
     __shared__ __align__(8) unsigned long long mbar[kMedianRing];
-    if (blockIdx.x == 0) median_wavefront_body<false>(prep, out, xchg, W, H, epoch, ring, mbar);
-    else                 median_wavefront_body<true>(prep, out, xchg, W, H, epoch, ring, mbar);
+    if (blockIdx.x == 0) median_wavefront_body<false>(prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
+    else                 median_wavefront_body<true>(prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
 }
 
 // `epoch` must differ between consecutive launches on the same exchange buffer (never 0: the buffer is
 // zero-initialised), so stale tags of the previous frame are never taken for current ones.
 // in: disparity map before the speckle decision; lab/size: speckle labels (or NULL: no speckle filter).
+// scratchRow: W floats that rows beyond the image write to (never read).
 static int launch_median3_inplace(const float* in, const int* lab, const int* size, int minArea, float* filteredTap, float* prep,
-                                  float* out, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st)
+                                  float* out, float* scratchRow, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st)
 {
     *epoch = (*epoch % 65535u) + 1u;
     const int groups = (H + 31) / 32;
     dim3 gp((W + kMedianTileW - 1) / kMedianTileW, groups);
     median_prepare<<<gp, 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
-    median_wavefront<<<groups, 32, 0, st>>>(prep, out, xchg, W, H, *epoch);
+    median_wavefront<<<groups, 32, 0, st>>>(prep, out, scratchRow, xchg, W, H, *epoch);
     return kMedianLaunches;
 }
 

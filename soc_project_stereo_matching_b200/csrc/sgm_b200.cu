@@ -70,6 +70,7 @@ struct Slot {
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
     unsigned long long* xchg = nullptr;   // median wavefront exchange rows [(H+31)/32][W]
     float* medianPrep = nullptr;      // sorted unfiltered inputs in wavefront order (postproc.cuh K5a)
+    float* medianScratch = nullptr;   // one row that the rows beyond the image of the last row group write to
     uint8_t* framePlanes = nullptr;   // SGMB_MatchFrame: left B,G,R then right B,G,R planes [6][N] (allocated on first use)
     float* depth = nullptr;           // SGMB_MatchFrame with calibration: depth map [N] (allocated on first use)
     unsigned medianEpoch = 0;
@@ -133,6 +134,7 @@ static void free_slot_buffers(Slot& s)
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
     cudaFree(s.pixL); s.pixL = nullptr;
+    cudaFree(s.medianScratch); s.medianScratch = nullptr;
     cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
     s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr;
@@ -388,6 +390,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.xchg, xbytes));
         CU(cudaMemset(s.xchg, 0, xbytes));
         // slots of idle (row, step) pairs are never written and must hold ordinary floats
+        CU(cudaMalloc(&s.medianScratch, ((size_t)W + 64) * sizeof(float)));
         CU(cudaMalloc(&s.medianPrep, median_prep_floats(W, H) * sizeof(float)));
         CU(cudaMemset(s.medianPrep, 0, median_prep_floats(W, H) * sizeof(float)));
         s.medianEpoch = 0;
@@ -548,7 +551,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     if (doMedian) {
         // the component sizes are applied while the median's inputs are gathered; dispSpeckle is a tap
         nk += launch_median3_inplace(cur, lab, lab ? lab + c->N : nullptr, c->opt.min_speckle_area, (taps && lab) ? s.dispSpeckle : nullptr,
-                                     s.medianPrep, s.dispFinal, s.xchg, &s.medianEpoch, W, H, s.stream);
+                                     s.medianPrep, s.dispFinal, s.medianScratch, s.xchg, &s.medianEpoch, W, H, s.stream);
         cur = s.dispFinal;
     }
     if (dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
