@@ -77,9 +77,9 @@ Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}
 |---|---|---|---|
 | K1 `sgm_census<5,5,uint32_t,false>` | (20,47,2) × 256 | ≈ 11 µs | 2 % |
 | K2 `sgm_aggregate_paths<4,16,8,8,2,uint32_t,false>` | 562 × 128 | ≈ 345 µs [{j['roofline']['kernel_ms']*1e3:.0f} µs event-timed inside the bench's timed region = {j['roofline']['kernel_share_of_step']*100:.0f} % of the step; 72 % of the ncu list's K1+K2+K3] | 66–72 % |
-| K3 `sgm_reduce_wta_lr<8,8,false>` | 375 × 256 | ≈ 127 µs | 26–30 % |
+| K3 `sgm_reduce_wta_lr<8,8,false>` | 375 × 256 | ≈ 124 µs | 26–30 % |
 | K4 `speckle_init` / `speckle_merge` / `speckle_count` | | 10 / 22 / 18 µs | (SGM_Match only) |
-| K5 `median_prepare` / `median_wavefront` | | 12 / 222 µs | (SGM_Match only) |
+| K5 `median_prepare` / `median_wavefront` | | 12 / 145 µs | (SGM_Match only) |
 | 9×7 census variants: `sgm_census<9,7,…>` / `sgm_aggregate_paths<4,16,4,16,2,u64,false>` | | 19 / 519 µs | |
 
 ## Roofline of the dominant kernel (K2), as `bench.py` reports it
@@ -90,7 +90,7 @@ Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}
   read-modify-writing a uint16 S, so the traffic is 4× *below* the algorithmic model — no wasted re-reads.
 * what binds it instead: ALU pipe {t['alu_pipe_pct']:.0f} %, XU (POPC) {t['xu_pipe_pct']:.0f} %, issue slots {t['issue_active_pct']:.0f} %, L1 data pipe ≈ 63 % of elapsed — none saturated;
   {t['warp_instructions']/1e6:.0f} M warp instructions in dependent chains with ≈ 3.8 warps per scheduler, plus the single-scoreboard prefetch wait (DESIGN.md §3.2).
-* K3 (`{tag}_ncu_full_sgm_reduce_wta.txt`): reads 479 MB → HBM floor 73 µs, measured 127 µs (57 % of its HBM roofline); ALU pipe 59 %, issue 61 %.
+* K3 (`{tag}_ncu_full_sgm_reduce_wta.txt`): reads 479 MB → HBM floor 73 µs, measured 124 µs (59 % of its HBM roofline); ALU pipe 59 %, issue 61 %.
 
 ## History
 | capture | `value` | ms per frame | K2 | `e2e` |
