@@ -67,7 +67,8 @@ if len(scal) > 1:
     for n, b, fn in scal:
         txt += (f"| {n} | {b['value']/1e3:.1f} | {b['ms_per_step']:.3f} | {b['value']/(n*j['value']):.3f} | {b['e2e']['value']/1e3:.1f} | "
                 f"{b['batched_c4']['value']/1e3:.1f} ({b['batched_c4']['frames_per_s']:.0f}) | `{fn}` |\n")
-    txt += "\n(N > 1 lines named `r1_g_*` were taken one commit before the CUDA-graph replay of the timed region; their N = 1 counterpart was 137.3 GDE/s.)\n"
+    if any(not fn.startswith(tag) for _, _, fn in scal):
+        txt += "\n(Lines from an earlier capture are named by that capture.)\n"
 txt += f"""
 Ratio `e2e` ÷ reference arm on the same box: {j['e2e']['value']/r['value']:.0f}× (the driver computes its own).
 
