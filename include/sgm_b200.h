@@ -91,8 +91,11 @@ int SGMB_Match(SGMB_Context* ctx, const uint8_t* img_left, const uint8_t* img_ri
 int SGMB_MatchDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int sync);
 int SGMB_Synchronize(SGMB_Context* ctx);
 
-/* Batch of n independent pairs, host pointers (pinned memory recommended: SGMB_HostAlloc), frames
- * pipelined over the context's slots: copy-in, kernels and copy-out of different frames overlap. */
+/* Batch of n independent pairs, host pointers, frames pipelined over the context's slots: copy-in, kernels and
+ * copy-out of different frames overlap.  Page-locked buffers (SGMB_HostAlloc / cudaHostAlloc / cudaHostRegister) are
+ * copied by the copy engine directly; pageable ones (malloc, static arrays) are staged through page-locked buffers
+ * owned by the slot.  All pointers are validated before anything is enqueued; after an error every slot is drained
+ * before the call returns, so no copy into a caller buffer is still in flight. */
 int SGMB_MatchBatch(SGMB_Context* ctx, const uint8_t* const* lefts, const uint8_t* const* rights,
                     float* const* disps, int n);
 /* Same with device-resident inputs and outputs (no PCIe traffic). */
@@ -177,11 +180,26 @@ int SGMB_TimeDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_r
 /* Run `iters` device-resident frames back to back on slot 0 without host synchronisation and time the whole region
  * with CUDA events on that stream (*total_ms); agg_ms (optional, [iters]) receives the duration of every
  * aggregation-kernel launch inside the region.  The frames are recorded into one CUDA graph (kernels, the side-buffer
- * memset, external event records for agg_ms) and replayed with a single launch; pipelines that include the in-place
- * median, whose exchange epoch changes per frame, are enqueued kernel by kernel instead (as is everything when the
+ * memsets, external event records for agg_ms) and replayed with a single launch (enqueued kernel by kernel when the
  * environment variable SGM_B200_NO_GRAPH is set). */
 int SGMB_RunDevice(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int iters,
                    float* total_ms, float* agg_ms);
+
+/* Same, replayed `replays` times (one graph launch each, every replay timed on its own: replay_ms[replays]); agg_ms
+ * (optional, [iters]) holds the aggregation-kernel durations of the last replay. */
+int SGMB_RunDeviceReplays(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int iters,
+                          int replays, float* replay_ms, float* agg_ms);
+
+/* Per-kernel durations of one device-resident frame of the current pipeline: CUDA events around every launch (direct
+ * launches, no graph), averaged over `iters` frames after `warmup` untimed ones, written to kernel_ms[0..capacity).
+ * Returns the number of kernels of the frame (or a negative error); SGMB_KernelName(ctx, k) names kernel k of the last call. */
+int SGMB_TimeKernels(SGMB_Context* ctx, const uint8_t* d_left, const uint8_t* d_right, float* d_disp, int warmup, int iters,
+                     float* kernel_ms, int capacity);
+const char* SGMB_KernelName(SGMB_Context* ctx, int index);
+
+/* The batch sharding rule of SGMB_MatchBatchMultiGPU / SGMB_PoolMatchBatch (host only, no CUDA call): device g of
+ * ndev processes the contiguous pairs [*lo, *hi) of n. */
+int SGMB_ShardRange(int n, int ndev, int g, int* lo, int* hi);
 
 /* The context behind SGM_Initialize/SGM_Match (NULL before the first SGM_Initialize), and the device it
  * will use (default 0, or env SGM_B200_DEVICE). */

@@ -133,6 +133,45 @@ def build_ref(w: int, h: int, d: int, variant: str = "", force: bool = False) ->
     return out
 
 
+DEMO_DIR = os.path.join(OUT, "demo")
+DEMO_EXE = os.path.join(DEMO_DIR, "bin", "sgm_demo")
+REF_DATA = "/root/reference/SemiGlobalMatching/Data"
+
+
+def build_demo(force: bool = False) -> str | None:
+    """Stage the drop-in acceptance run: the reference's UNMODIFIED demo driver main.c, compiled
+    against include/SemiGlobalMatching.h and linked to libsgm_b200.so INSTEAD of the reference's SemiGlobalMatching.c,
+    plus the two cone images it loads from ../Data/cone/ (main.c:19-20).  Everything goes to oracle/_ref/demo/ (git-ignored,
+    shipped to the GPU box); the rpath is relative so the binary finds the library wherever the tree is unpacked.
+    Returns the executable's path, or None when neither the reference tree nor a previously staged copy exists."""
+    if not reference_available():
+        return DEMO_EXE if os.path.isfile(DEMO_EXE) else None
+    root = os.path.dirname(HERE)
+    include = os.path.join(root, "include")
+    libdir = os.path.join(root, "soc_project_stereo_matching_b200", "lib")
+    main_c = os.path.join(REF_DIR, "main.c")
+    data_dst = os.path.join(DEMO_DIR, "Data", "cone")
+    if not force and _newer(DEMO_EXE, main_c, os.path.join(include, "SemiGlobalMatching.h"), os.path.abspath(__file__)) \
+            and os.path.isfile(os.path.join(data_dst, "im6.png")):
+        return DEMO_EXE
+    os.makedirs(os.path.dirname(DEMO_EXE), exist_ok=True)
+    os.makedirs(data_dst, exist_ok=True)
+    import shutil
+    for name in ("im2.png", "im6.png"):
+        shutil.copyfile(os.path.join(REF_DATA, "cone", name), os.path.join(data_dst, name))
+    with tempfile.TemporaryDirectory(prefix="sgm_demo_build_") as tmp:
+        # main.c includes "SemiGlobalMatching.h" relative to its own directory; a one-line wrapper puts OUR header (same
+        # include guard) in front of it, so the demo source itself is compiled byte for byte as it lies in the reference
+        wrapper = os.path.join(tmp, "demo.c")
+        with open(wrapper, "w") as f:
+            f.write(f'#include "{include}/SemiGlobalMatching.h"\n#include "{main_c}"\n')
+        cmd = ["gcc", "-O2", "-std=gnu11", "-w", f"-I{REF_DIR}", "-o", DEMO_EXE + ".tmp", wrapper, f"-L{libdir}", "-lsgm_b200",
+               "-Wl,-rpath,$ORIGIN/../../../../soc_project_stereo_matching_b200/lib", "-lm"]
+        subprocess.run(cmd, check=True)
+    os.replace(DEMO_EXE + ".tmp", DEMO_EXE)
+    return DEMO_EXE
+
+
 def main(argv: list[str]) -> int:
     if "--oracle" in argv or len(argv) == 0:
         print(build_oracle(force=True))

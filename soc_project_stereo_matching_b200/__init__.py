@@ -109,6 +109,10 @@ def _load() -> C.CDLL:
         "SGMB_LastDeviceMs": (C.c_float, [vp]),
         "SGMB_TimeDevice": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
         "SGMB_RunDevice": (i32, [vp, vp, vp, vp, i32, vp, vp]),
+        "SGMB_RunDeviceReplays": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
+        "SGMB_TimeKernels": (i32, [vp, vp, vp, vp, i32, i32, vp, i32]),
+        "SGMB_KernelName": (C.c_char_p, [vp, i32]),
+        "SGMB_ShardRange": (i32, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "SGMB_GlobalContext": (vp, []),
         "SGMB_SetGlobalDevice": (i32, [i32]),
         "SGMB_DebugWalkPath": (i32, [i32, i32, i32, i32, vp, i32]),
@@ -169,6 +173,8 @@ def SGM_Match(img_left: np.ndarray | None, img_right: np.ndarray | None, disp_le
     ``disp_left`` must be a C-contiguous float32 array of width*height elements; it is overwritten."""
     if disp_left.dtype != np.float32 or not disp_left.flags.c_contiguous:
         raise TypeError("disp_left must be a C-contiguous float32 array")
+    if _state["shape"] is not None and disp_left.size != _state["shape"][0] * _state["shape"][1]:
+        raise ValueError("disp_left must hold width*height floats (the library writes that many)")
     keep = []
     ptrs = []
     for img in (img_left, img_right):
@@ -266,7 +272,7 @@ class Context:
 
     def match_batch(self, lefts: np.ndarray, rights: np.ndarray) -> np.ndarray:
         """lefts/rights: uint8 [n, H, W] -> float32 [n, H, W]."""
-        l = np.ascontiguousarray(lefts, np.uint8); r = np.ascontiguousarray(rights, np.uint8)
+        l, r = _batch_arrays(lefts, rights, self.height, self.width)
         n = l.shape[0]
         out = np.empty((n, self.height, self.width), np.float32)
         self.match_batch_ptrs([l[k].ctypes.data for k in range(n)], [r[k].ctypes.data for k in range(n)],
@@ -348,6 +354,20 @@ class Context:
         return frame, agg
 
 
+    def run_device_replays(self, d_left: int, d_right: int, d_out: int, iters: int, replays: int):
+        """-> (milliseconds of each of `replays` launches of one graph of `iters` frames, aggregation-kernel ms of the last)."""
+        rep = np.zeros(replays, np.float32); agg = np.zeros(iters, np.float32)
+        _check(lib.SGMB_RunDeviceReplays(self._h, d_left, d_right, d_out, iters, replays, rep.ctypes.data, agg.ctypes.data))
+        return rep, agg
+
+    def time_kernels(self, d_left: int, d_right: int, d_out: int, warmup: int = 3, iters: int = 20) -> list[tuple[str, float]]:
+        """-> [(kernel name, mean milliseconds)] of one frame of the current pipeline (CUDA events around every launch)."""
+        ms = np.zeros(16, np.float32)
+        n = lib.SGMB_TimeKernels(self._h, d_left, d_right, d_out, warmup, iters, ms.ctypes.data, ms.size)
+        if n < 0:
+            raise SGMError(n)
+        return [(lib.SGMB_KernelName(self._h, k).decode(), float(ms[k])) for k in range(n)]
+
     def run_device(self, d_left: int, d_right: int, d_out: int, iters: int, time_aggregation: bool = True):
         """-> (total milliseconds of `iters` back-to-back frames, per-launch aggregation-kernel ms)."""
         total = C.c_float(0)
@@ -357,8 +377,22 @@ class Context:
         return float(total.value), agg
 
 
-def match_batch_multi_gpu(devices, slots_per_device, width, height, option, pipeline, lefts, rights) -> np.ndarray:
+def shard_range(n: int, ndev: int, g: int) -> tuple[int, int]:
+    """The library's batch sharding rule (SGMB_ShardRange, host only): device g of ndev takes pairs [lo, hi) of n."""
+    lo, hi = C.c_int(), C.c_int()
+    _check(lib.SGMB_ShardRange(n, ndev, g, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def _batch_arrays(lefts, rights, height: int, width: int):
     l = np.ascontiguousarray(lefts, np.uint8); r = np.ascontiguousarray(rights, np.uint8)
+    if l.ndim != 3 or l.shape != r.shape or l.shape[1:] != (height, width):
+        raise ValueError(f"lefts / rights must both have shape (n, {height}, {width}); got {l.shape} and {r.shape}")
+    return l, r
+
+
+def match_batch_multi_gpu(devices, slots_per_device, width, height, option, pipeline, lefts, rights) -> np.ndarray:
+    l, r = _batch_arrays(lefts, rights, height, width)
     n = l.shape[0]
     out = np.empty((n, height, width), np.float32)
     dev = (C.c_int * len(devices))(*devices)
@@ -396,7 +430,7 @@ class Pool:
         self.width, self.height = width, height
 
     def match_batch(self, lefts: np.ndarray, rights: np.ndarray) -> np.ndarray:
-        l = np.ascontiguousarray(lefts, np.uint8); r = np.ascontiguousarray(rights, np.uint8)
+        l, r = _batch_arrays(lefts, rights, self.height, self.width)
         n = l.shape[0]
         out = np.empty((n, self.height, self.width), np.float32)
         pa = lambda a: (C.c_void_p * n)(*[a[k].ctypes.data for k in range(n)])

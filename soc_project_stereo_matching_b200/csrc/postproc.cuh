@@ -128,16 +128,21 @@ __global__ void __launch_bounds__(32) speckle_count(int* lab, int* size, int W, 
 // speckle_apply when the median is switched off).
 constexpr int kSpeckleLabelLaunches = 3;
 
-static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, int W, int H, float diff, cudaStream_t st)
+// `mark(name)` is called after every launch (per-kernel timing hook of the host layer; a no-op otherwise).
+template <typename Mark>
+static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, int W, int H, float diff, cudaStream_t st, Mark mark)
 {
     const int n = W * H;
     int* lab = scratch;
     int* size = scratch + n;
     dim3 gseg((W + 31) / 32, H);
     speckle_init<<<gseg, 32, 0, st>>>(in, lab, size, W, H, diff);
+    mark("speckle_init");
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     speckle_merge<<<g, b, 0, st>>>(in, lab, W, H, diff);
+    mark("speckle_merge");
     speckle_count<<<gseg, 32, 0, st>>>(lab, size, W, H);
+    mark("speckle_count");
     return kSpeckleLabelLaunches;
 }
 
@@ -183,8 +188,12 @@ __global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ 
 //       __shfl_up_sync exactly one step after it was produced.  Between warps (row 32g-1 -> row 32g) the
 //       producer's last lane publishes (tag, value) as one 64-bit word per column in a global exchange row; the
 //       consumer fetches 32 columns per coalesced load, one batch ahead of use, and re-polls only if a tag is
-//       stale.  Producers never wait, all CTAs are co-resident (<= 2048 one-warp CTAs) and every dependency
-//       points to a lower block index, so this cannot deadlock.
+//       stale.  Producers never wait and every dependency points to the previous ROW GROUP.  A CTA takes its row group
+//       from a ticket counter (atomicAdd when it starts running), not from blockIdx: whatever order the hardware
+//       dispatches CTAs in, the group a CTA waits for was taken by a CTA that is already running, so the chain of
+//       waits always ends at a running CTA even when not all CTAs are co-resident (40 KB of shared memory per CTA
+//       allow ~5 per SM, ~740 per device; H = 65535 has 2048 groups).  The poll loop is bounded: a CTA that has
+//       waited ~2 s traps instead of hanging the device.
 constexpr int kMedianLaunches = 2;
 constexpr int kMedianTileW = 64;      // K5a: columns per block
 // One bulk copy per 32 steps: the per-block bookkeeping (mbarrier wait, warp syncs, proxy fence, re-arming the copy) costs
@@ -320,7 +329,7 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
 }
 
 template <bool HAS_ABOVE>
-__device__ __forceinline__ void median_wavefront_body(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow,
+__device__ __forceinline__ void median_wavefront_body(const int g, const float* __restrict__ prep, float* __restrict__ out, float* scratchRow,
                                                       unsigned long long* xchg, int W, int H, unsigned epoch,
                                                       float (*ring)[kMedianBlockSteps][5][32], unsigned long long* mbar)
 {
@@ -329,7 +338,6 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
     static_assert(NR % NB == 0 && NR >= NB, "ring must hold whole batches");
     constexpr unsigned kBlockBytes = BS * kMedianStepBytes;
     const int lane = threadIdx.x;
-    const int g = blockIdx.x;
     const int i = 32 * g + lane;
     const int Wrow = W;                                                       // rows beyond the image (last group) run like the others and write to a scratch row
     const bool publishes = (lane == 31) && (32 * (g + 1) < H);                // someone consumes this row
@@ -381,8 +389,10 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
 #ifdef SGM_MEDIAN_DEBUG
             long long w0 = clock64();
 #endif
+            unsigned spins = 0;
             while (!__all_sync(FULL, !inRow || (unsigned)(v >> 32) == (tagBase | (unsigned)(col + 1)))) {
                 __nanosleep(200);                        // do not hammer the L2 line the producer is storing to
+                if (++spins > (1u << 23)) __trap();      // ~2 s without progress: fail the launch instead of hanging the device
                 v = inRow ? ld_relaxed_gpu_u64(aboveX + col) : 0ull;
 #ifdef SGM_MEDIAN_DEBUG
                 ++pollCount;
@@ -428,28 +438,40 @@ __device__ __forceinline__ void median_wavefront_body(const float* __restrict__ 
 #endif
 }
 
+// `ticket`: zeroed before every launch (it lives behind the exchange rows and is cleared with them).
 __global__ void __launch_bounds__(32)
-median_wavefront(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow, unsigned long long* xchg, int W, int H,
-                 unsigned epoch)
+median_wavefront(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow, unsigned long long* xchg, int* ticket,
+                 int W, int H, unsigned epoch)
 {
     __shared__ __align__(128) float ring[kMedianRing][kMedianBlockSteps][5][32];
     __shared__ __align__(8) unsigned long long mbar[kMedianRing];
-    if (blockIdx.x == 0) median_wavefront_body<false>(prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
-    else                 median_wavefront_body<true>(prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
+    int g = 0;
+    if (threadIdx.x == 0) g = atomicAdd(ticket, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g == 0) median_wavefront_body<false>(g, prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
+    else        median_wavefront_body<true>(g, prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
 }
+
+// Bytes of the exchange buffer: one 64-bit (tag, value) word per column and row group, then the ticket counter.
+static size_t median_xchg_bytes(int W, int H) { return ((size_t)((H + 31) / 32) * W + 1) * sizeof(unsigned long long); }
 
 // `epoch` must differ between consecutive launches on the same exchange buffer (never 0: the buffer is
 // zero-initialised), so stale tags of the previous frame are never taken for current ones.
 // in: disparity map before the speckle decision; lab/size: speckle labels (or NULL: no speckle filter).
 // scratchRow: W floats that rows beyond the image write to (never read).
+template <typename Mark>
 static int launch_median3_inplace(const float* in, const int* lab, const int* size, int minArea, float* filteredTap, float* prep,
-                                  float* out, float* scratchRow, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st)
+                                  float* out, float* scratchRow, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st,
+                                  Mark mark)
 {
     *epoch = (*epoch % 65535u) + 1u;
     const int groups = (H + 31) / 32;
     dim3 gp((W + kMedianTileW - 1) / kMedianTileW, groups);
     median_prepare<<<gp, 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
-    median_wavefront<<<groups, 32, 0, st>>>(prep, out, scratchRow, xchg, W, H, *epoch);
+    mark("median_prepare");
+    int* ticket = reinterpret_cast<int*>(xchg + (size_t)groups * W);
+    median_wavefront<<<groups, 32, 0, st>>>(prep, out, scratchRow, xchg, ticket, W, H, *epoch);
+    mark("median_wavefront");
     return kMedianLaunches;
 }
 

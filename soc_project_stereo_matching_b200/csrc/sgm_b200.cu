@@ -50,9 +50,16 @@ static int fail(int code, const char* fmt, ...)
 extern "C" const char* SGMB_LastError(void) { return g_err; }
 
 // ------------------------------------------------------------------------------------------------ context
+constexpr int kMaxTimedKernels = 16;
+struct KernelTimer {                  // one event before the first launch, one after every launch
+    cudaEvent_t ev[kMaxTimedKernels + 1] = {};
+    const char* name[kMaxTimedKernels] = {};
+    int n = 0;
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t evStart = nullptr, evStop = nullptr, evAgg0 = nullptr, evAgg1 = nullptr, evDone = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evAgg0 = nullptr, evAgg1 = nullptr, evDone = nullptr, evCopied = nullptr;
     uint8_t* img[2] = {nullptr, nullptr};
     void* censusL = nullptr;          // descriptors: uint32 (5x5 census) or 64-bit (9x7 census)
     void* censusR4 = nullptr;         // [16 / descBytes][copyStride] shifted copies (census.cuh)
@@ -78,6 +85,12 @@ struct Slot {
     // kernels) is recorded once into a CUDA graph and replayed by every later call until the configuration changes
     cudaGraphExec_t frameExec = nullptr;
     bool busy = false;
+    // Pageable caller memory (malloc / static arrays, e.g. the reference demo main.c:25-26,81) is staged through page-locked
+    // buffers owned by the slot (allocated on first use): stageIn = both images in the layout of img[], stageOut = result.
+    uint8_t* stageIn = nullptr;
+    float* stageOut = nullptr;
+    float* pendingOut = nullptr;      // pageable destination that stageOut still has to be copied to (after the stream drained)
+    KernelTimer* timer = nullptr;     // SGMB_TimeKernels: events around every launch of enqueue_frame
 };
 
 struct SGMB_Context {
@@ -93,6 +106,7 @@ struct SGMB_Context {
     int greyFormula = SGMB_GREY_BOARD; // SGMB_MatchFrame: weights of the colour -> grey conversion
     CompareAcc* cmpScratch = nullptr; // SGMB_CompareDepth*: per-block partials + result
     size_t N = 0;
+    size_t imgStride = 0;             // bytes between the left and the right image of a slot (N + 16 rounded up to 256)
     int padF = 0;
     size_t copyStride = 0, planeStride = 0;
     // configuration-wide read-only device tables
@@ -114,6 +128,7 @@ struct SGMB_Context {
     float lastMs = 0.f;
     bool tapsAllocated = false;
     bool capturing = false;       // enqueue_frame is being recorded into a CUDA graph (SGMB_RunDevice)
+    const char* timedName[kMaxTimedKernels] = {};   // kernel names of the last SGMB_TimeKernels call
 };
 
 static int ensure_device(SGMB_Context* c)
@@ -130,7 +145,10 @@ static void drop_frame_graph(Slot& s)
 static void free_slot_buffers(Slot& s)
 {
     drop_frame_graph(s);
-    cudaFree(s.img[0]); cudaFree(s.img[1]); cudaFree(s.censusL); cudaFree(s.censusR4); cudaFree(s.planes);
+    cudaFree(s.img[0]); cudaFree(s.censusL);
+    if (s.stageIn) cudaFreeHost(s.stageIn);
+    if (s.stageOut) cudaFreeHost(s.stageOut);
+    s.stageIn = nullptr; s.stageOut = nullptr; s.pendingOut = nullptr; cudaFree(s.censusR4); cudaFree(s.planes);
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
     cudaFree(s.pixL); s.pixL = nullptr;
@@ -170,13 +188,18 @@ extern "C" int SGMB_Create(SGMB_Context** out, int device, int slots)
     c->device = device;
     c->nslots = slots;
     c->slots.resize(slots);
-    CU(cudaSetDevice(device));
-    for (auto& s : c->slots) {
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU(cudaEventCreate(&s.evStart)); CU(cudaEventCreate(&s.evStop));
-        CU(cudaEventCreate(&s.evAgg0)); CU(cudaEventCreate(&s.evAgg1));
-        CU(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
-    }
+    const int rc = [&]() -> int {
+        CU(cudaSetDevice(device));
+        for (auto& s : c->slots) {
+            CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CU(cudaEventCreate(&s.evStart)); CU(cudaEventCreate(&s.evStop));
+            CU(cudaEventCreate(&s.evAgg0)); CU(cudaEventCreate(&s.evAgg1));
+            CU(cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.evCopied, cudaEventDisableTiming));
+        }
+        return SGMB_OK;
+    }();
+    if (rc != SGMB_OK) { SGMB_Destroy(c); return rc; }      // releases whatever was created (g_err keeps the reason)
     *out = c;
     return SGMB_OK;
 }
@@ -195,6 +218,7 @@ extern "C" void SGMB_Destroy(SGMB_Context* c)
         if (s.evAgg0) cudaEventDestroy(s.evAgg0);
         if (s.evAgg1) cudaEventDestroy(s.evAgg1);
         if (s.evDone) cudaEventDestroy(s.evDone);
+        if (s.evCopied) cudaEventDestroy(s.evCopied);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete c;
@@ -258,10 +282,14 @@ static int wta_prepare(SGMB_Context* c)
     c->wtaCPP = CPP;
     c->wtaTW = WtaShape<CPP>::kTW;
     c->wtaSmem = (size_t)(2 * c->wtaTW + c->D) * WtaShape<CPP>::kRS * sizeof(uint16_t);
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
-    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wtaSmem));
+    // The attribute belongs to the function on this device, i.e. to every context of the process: it is set to the largest
+    // ring of the CPP class (D = 16 * CPP), never to this context's own size - a later context with a smaller D must not
+    // lower the limit under a live context with a larger one.
+    const int classMax = (2 * WtaShape<CPP>::kTW + 16 * CPP) * WtaShape<CPP>::kRS * (int)sizeof(uint16_t);
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
+    CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
     return SGMB_OK;
 }
 
@@ -283,6 +311,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->opt = *option;
     c->W = width; c->H = height; c->D = D;
     c->N = (size_t)width * height;
+    c->imgStride = (c->N + 16 + 255) & ~(size_t)255;
     c->NR = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
     c->descBytes = (c->censusW == 9 && c->censusH == 7) ? 8 : 4;
     const int nCopies = 16 / c->descBytes;
@@ -371,7 +400,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
 
     // ---- per-slot device buffers
     for (auto& s : c->slots) {
-        CU(cudaMalloc(&s.img[0], c->N + 16)); CU(cudaMalloc(&s.img[1], c->N + 16));
+        CU(cudaMalloc(&s.img[0], 2 * c->imgStride));            // left and right image in one allocation: one H2D copy from staging
+        s.img[1] = s.img[0] + c->imgStride;
         CU(cudaMalloc(&s.censusL, c->N * (size_t)c->descBytes));
         CU(cudaMalloc(&s.censusR4, nCopies * c->copyStride * (size_t)c->descBytes));
         CU(cudaMemset(s.censusR4, 0, nCopies * c->copyStride * (size_t)c->descBytes));
@@ -386,7 +416,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.dispSpeckle, c->N * sizeof(float)));
         CU(cudaMalloc(&s.dispFinal, c->N * sizeof(float)));
         CU(cudaMalloc(&s.labels, 2 * c->N * sizeof(int32_t)));
-        const size_t xbytes = (size_t)((H + 31) / 32) * W * sizeof(unsigned long long);
+        const size_t xbytes = median_xchg_bytes(W, H);
         CU(cudaMalloc(&s.xchg, xbytes));
         CU(cudaMemset(s.xchg, 0, xbytes));
         // slots of idle (row, step) pairs are never written and must hold ordinary floats
@@ -441,15 +471,25 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     const bool doSpeckle = (c->pipeline & SGMB_PIPE_SPECKLE) && c->opt.is_remove_speckles;
     const bool doMedian = (c->pipeline & SGMB_PIPE_MEDIAN) != 0;
     int nk = 0;
+    // SGMB_TimeKernels: an event before the first launch and one after every launch (never while capturing a graph)
+    KernelTimer* tm = c->capturing ? nullptr : s.timer;
+    if (tm) tm->n = 0;
+    auto mark = [&](const char* name) -> int {
+        if (!tm || tm->n >= kMaxTimedKernels) return SGMB_OK;
+        tm->name[tm->n] = name;
+        CU(cudaEventRecord(tm->ev[++tm->n], s.stream));
+        return SGMB_OK;
+    };
 
     if (c->nEntries > 0) CU(cudaMemsetAsync(s.side, 0, (size_t)c->nEntries * c->Dp * sizeof(uint16_t), s.stream));
     if (doMedian) {
         // the wavefront's exchange rows are cleared every frame (a few hundred KB, long before they are used), so the tag
         // epoch can stay constant and the frame has no per-launch kernel argument: it can be replayed as a CUDA graph
-        CU(cudaMemsetAsync(s.xchg, 0, (size_t)((H + 31) / 32) * W * sizeof(unsigned long long), s.stream));
+        CU(cudaMemsetAsync(s.xchg, 0, median_xchg_bytes(W, H), s.stream));       // exchange rows + the row-group ticket
         s.medianEpoch = 0;
     }
 
+    if (tm) CU(cudaEventRecord(tm->ev[0], s.stream));
     {   // K1 census
         CensusParams p{};
         p.img[0] = dL; p.img[1] = dR; p.left = s.censusL; p.right4 = s.censusR4;
@@ -467,6 +507,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
             else        sgm_census<9, 7, desc64_t, false><<<grid, threads, 0, s.stream>>>(p);
         }
         ++nk;
+        if (int rc = mark("sgm_census")) return rc;
         if (planar) dL = s.img[0];       // K2 reads the left grey image (adaptive P2, SemiGlobalMatching.c:335)
     }
     {   // K2 aggregation
@@ -505,6 +546,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
 #undef SGM_AGG_LAUNCH
         if (timeAgg) CU(cudaEventRecordWithFlags(s.evAgg1, s.stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ++nk;
+        if (int rc = mark("sgm_aggregate_paths")) return rc;
     }
     float* lrOut = s.dispLR;
     {   // K3 plane sum + WTA + LR
@@ -536,22 +578,24 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         }
 #undef SGM_WTA_LAUNCH
         ++nk;
+        if (int rc = mark("sgm_reduce_wta_lr")) return rc;
     }
     float* cur = lrOut;
     const int32_t* lab = nullptr;
     if (doSpeckle) {
-        nk += launch_speckle_labels(cur, s.labels, W, H, 1.0f, s.stream);
+        nk += launch_speckle_labels(cur, s.labels, W, H, 1.0f, s.stream, mark);
         lab = s.labels;
         if (!doMedian) {
             speckle_apply<<<((int)c->N + 255) / 256, 256, 0, s.stream>>>(cur, s.dispSpeckle, lab, lab + c->N, (int)c->N, c->opt.min_speckle_area);
             ++nk;
+            if (int rc = mark("speckle_apply")) return rc;
             cur = s.dispSpeckle;
         }
     }
     if (doMedian) {
         // the component sizes are applied while the median's inputs are gathered; dispSpeckle is a tap
         nk += launch_median3_inplace(cur, lab, lab ? lab + c->N : nullptr, c->opt.min_speckle_area, (taps && lab) ? s.dispSpeckle : nullptr,
-                                     s.medianPrep, s.dispFinal, s.medianScratch, s.xchg, &s.medianEpoch, W, H, s.stream);
+                                     s.medianPrep, s.dispFinal, s.medianScratch, s.xchg, &s.medianEpoch, W, H, s.stream, mark);
         cur = s.dispFinal;
     }
     if (dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
@@ -591,21 +635,84 @@ static float* frame_result(SGMB_Context* c, Slot& s)
     return doMedian ? s.dispFinal : (doSpeckle ? s.dispSpeckle : s.dispLR);
 }
 
+// ------------------------------------------------------------------------------------------------ host <-> device copies
+// Page-locked caller memory (cudaHostAlloc / cudaHostRegister / SGMB_HostAlloc) is read and written by the copy engine
+// directly.  Pageable memory (malloc, static arrays: what the reference demo passes, main.c:25-26,81) makes
+// cudaMemcpyAsync stage synchronously inside the driver; here it goes through the slot's own page-locked staging buffers
+// instead: one memcpy + ONE asynchronous copy for both images, and the result is copied out of the staging buffer once the
+// stream has drained.  SGM_B200_PAGEABLE=direct hands pageable pointers to cudaMemcpyAsync as they are (measurement aid).
+static bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static bool pageable_direct()
+{
+    static const bool v = [] { const char* e = getenv("SGM_B200_PAGEABLE"); return e && !strcmp(e, "direct"); }();
+    return v;
+}
+
+// Result of the slot's previous frame still sitting in the staging buffer -> the caller's pageable buffer.
+static int flush_pending_out(SGMB_Context* c, Slot& s)
+{
+    if (!s.pendingOut) return SGMB_OK;
+    CU(cudaStreamSynchronize(s.stream));
+    memcpy(s.pendingOut, s.stageOut, c->N * sizeof(float));
+    s.pendingOut = nullptr;
+    return SGMB_OK;
+}
+
+static int copy_in(SGMB_Context* c, Slot& s, const uint8_t* L, const uint8_t* R)
+{
+    if (int rc = flush_pending_out(c, s)) return rc;
+    if (pageable_direct() || (host_is_pinned(L) && host_is_pinned(R))) {
+        CU(cudaMemcpyAsync(s.img[0], L, c->N, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.img[1], R, c->N, cudaMemcpyHostToDevice, s.stream));
+        return SGMB_OK;
+    }
+    if (!s.stageIn) CU(cudaHostAlloc(reinterpret_cast<void**>(&s.stageIn), 2 * c->imgStride, cudaHostAllocDefault));
+    else CU(cudaEventSynchronize(s.evCopied));       // the previous copy out of stageIn must have finished
+    memcpy(s.stageIn, L, c->N);
+    memcpy(s.stageIn + c->imgStride, R, c->N);
+    CU(cudaMemcpyAsync(s.img[0], s.stageIn, c->imgStride + c->N, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaEventRecord(s.evCopied, s.stream));
+    return SGMB_OK;
+}
+
+// Enqueue the copy of the slot's result to `out`; for pageable `out` the last step (staging -> out) happens in
+// flush_pending_out(), which every path calls before it returns to the caller or reuses the slot.
+static int copy_out(SGMB_Context* c, Slot& s, float* out)
+{
+    if (pageable_direct() || host_is_pinned(out)) {
+        CU(cudaMemcpyAsync(out, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        return SGMB_OK;
+    }
+    if (!s.stageOut) CU(cudaHostAlloc(reinterpret_cast<void**>(&s.stageOut), c->N * sizeof(float), cudaHostAllocDefault));
+    CU(cudaMemcpyAsync(s.stageOut, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    s.pendingOut = out;
+    return SGMB_OK;
+}
+
 extern "C" int SGMB_Match(SGMB_Context* c, const uint8_t* L, const uint8_t* R, float* out)
 {
     if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_Match: context is not configured");   // SemiGlobalMatching.c:70-72
     if (!L || !R) return fail(SGMB_E_ARG, "SGMB_Match: NULL image");                                 // SemiGlobalMatching.c:73-75
     if (int rc = ensure_device(c)) return rc;
     Slot& s = c->slots[0];
-    CU(cudaEventRecord(s.evStart, s.stream));
-    CU(cudaMemcpyAsync(s.img[0], L, c->N, cudaMemcpyHostToDevice, s.stream));
-    CU(cudaMemcpyAsync(s.img[1], R, c->N, cudaMemcpyHostToDevice, s.stream));
-    if (int rc = launch_slot_frame(c, s)) return rc;
-    if (out) CU(cudaMemcpyAsync(out, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaEventRecord(s.evStop, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
-    CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
-    return SGMB_OK;
+    const int rc = [&]() -> int {
+        CU(cudaEventRecord(s.evStart, s.stream));
+        if (int rc = copy_in(c, s, L, R)) return rc;
+        if (int rc = launch_slot_frame(c, s)) return rc;
+        if (out) if (int rc = copy_out(c, s, out)) return rc;
+        CU(cudaEventRecord(s.evStop, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+        return flush_pending_out(c, s);
+    }();
+    if (rc != SGMB_OK) { cudaStreamSynchronize(s.stream); s.pendingOut = nullptr; }
+    return rc;
 }
 
 extern "C" int SGMB_MatchDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int sync)
@@ -637,30 +744,38 @@ static int run_batch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* c
 {
     if (!c || !c->configured) return fail(SGMB_E_STATE, "batch: context is not configured");
     if (n < 0 || (n > 0 && (!Ls || !Rs || !outs))) return fail(SGMB_E_ARG, "batch: bad arguments");
+    // every pointer is checked before anything is enqueued: a bad pair must not leave earlier pairs running
+    for (int k = 0; k < n; ++k)
+        if (!Ls[k] || !Rs[k] || !outs[k]) return fail(SGMB_E_ARG, "batch: NULL pointer at pair %d", k);
     if (int rc = ensure_device(c)) return rc;
     Slot& s0 = c->slots[0];
-    CU(cudaEventRecord(s0.evStart, s0.stream));
-    for (int k = 0; k < n; ++k) {
-        if (!Ls[k] || !Rs[k] || !outs[k]) return fail(SGMB_E_ARG, "batch: NULL pointer at pair %d", k);
-        Slot& s = c->slots[k % c->nslots];
-        if (k == 0) { for (int j = 1; j < c->nslots; ++j) CU(cudaStreamWaitEvent(c->slots[j].stream, s0.evStart, 0)); }
-        if (deviceMem) {
-            if (int rc = enqueue_frame(c, s, Ls[k], Rs[k], outs[k], false, nullptr)) return rc;
-        } else {
-            CU(cudaMemcpyAsync(s.img[0], Ls[k], c->N, cudaMemcpyHostToDevice, s.stream));
-            CU(cudaMemcpyAsync(s.img[1], Rs[k], c->N, cudaMemcpyHostToDevice, s.stream));
-            if (int rc = launch_slot_frame(c, s)) return rc;
-            CU(cudaMemcpyAsync(outs[k], frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    // On a CUDA error in the middle of the batch the work already enqueued (kernels, asynchronous copies into the caller's
+    // buffers) is drained before the caller gets control back.
+    const int rc = [&]() -> int {
+        CU(cudaEventRecord(s0.evStart, s0.stream));
+        for (int j = 1; j < c->nslots && n > 0; ++j) CU(cudaStreamWaitEvent(c->slots[j].stream, s0.evStart, 0));
+        for (int k = 0; k < n; ++k) {
+            Slot& s = c->slots[k % c->nslots];
+            if (deviceMem) {
+                if (int rc = enqueue_frame(c, s, Ls[k], Rs[k], outs[k], false, nullptr)) return rc;
+            } else {
+                if (int rc = copy_in(c, s, Ls[k], Rs[k])) return rc;
+                if (int rc = launch_slot_frame(c, s)) return rc;
+                if (int rc = copy_out(c, s, outs[k])) return rc;
+            }
         }
-    }
-    for (int j = 1; j < c->nslots; ++j) {
-        CU(cudaEventRecord(c->slots[j].evDone, c->slots[j].stream));
-        CU(cudaStreamWaitEvent(s0.stream, c->slots[j].evDone, 0));
-    }
-    CU(cudaEventRecord(s0.evStop, s0.stream));
-    CU(cudaStreamSynchronize(s0.stream));
-    CU(cudaEventElapsedTime(&c->lastMs, s0.evStart, s0.evStop));
-    return SGMB_OK;
+        for (int j = 1; j < c->nslots; ++j) {
+            CU(cudaEventRecord(c->slots[j].evDone, c->slots[j].stream));
+            CU(cudaStreamWaitEvent(s0.stream, c->slots[j].evDone, 0));
+        }
+        CU(cudaEventRecord(s0.evStop, s0.stream));
+        CU(cudaStreamSynchronize(s0.stream));
+        CU(cudaEventElapsedTime(&c->lastMs, s0.evStart, s0.evStop));
+        for (auto& s : c->slots) if (int rc = flush_pending_out(c, s)) return rc;
+        return SGMB_OK;
+    }();
+    if (rc != SGMB_OK) for (auto& s : c->slots) { cudaStreamSynchronize(s.stream); s.pendingOut = nullptr; }
+    return rc;
 }
 
 extern "C" int SGMB_MatchBatch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* const* Rs, float* const* outs, int n)
@@ -673,6 +788,15 @@ extern "C" int SGMB_MatchBatchDevice(SGMB_Context* c, const uint8_t* const* Ls, 
     return run_batch(c, Ls, Rs, outs, n, true);
 }
 
+// The one statement of the batch sharding rule: device g of ndev takes the contiguous pairs [lo, hi) of n.
+extern "C" int SGMB_ShardRange(int n, int ndev, int g, int* lo, int* hi)
+{
+    if (n < 0 || ndev < 1 || g < 0 || g >= ndev || !lo || !hi) return fail(SGMB_E_ARG, "SGMB_ShardRange: bad arguments");
+    *lo = (int)((long long)n * g / ndev);
+    *hi = (int)((long long)n * (g + 1) / ndev);
+    return SGMB_OK;
+}
+
 extern "C" int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots, uint16_t width, uint16_t height,
                                        const SGMOption* option, unsigned flags, const uint8_t* const* Ls,
                                        const uint8_t* const* Rs, float* const* outs, int n)
@@ -683,7 +807,8 @@ extern "C" int SGMB_MatchBatchMultiGPU(const int* devices, int ndev, int slots, 
     std::vector<std::thread> th;
     for (int g = 0; g < ndev; ++g) {
         th.emplace_back([&, g]() {
-            const int lo = (int)((long long)n * g / ndev), hi = (int)((long long)n * (g + 1) / ndev);   // contiguous shard
+            int lo = 0, hi = 0;
+            SGMB_ShardRange(n, ndev, g, &lo, &hi);
             SGMB_Context* ctx = nullptr;
             int rc = SGMB_Create(&ctx, devices[g], slots);
             if (!rc) rc = SGMB_SetPipeline(ctx, flags);
@@ -771,7 +896,8 @@ extern "C" int SGMB_PoolMatchBatch(SGMB_Pool* p, const uint8_t* const* lefts, co
     if (!p) return fail(SGMB_E_ARG, "NULL pool");
     const int ndev = (int)p->ctx.size();
     return pool_for_each(p, [&](SGMB_Context* c, int g) {
-        const int lo = (int)((long long)n * g / ndev), hi = (int)((long long)n * (g + 1) / ndev);   // contiguous shard
+        int lo = 0, hi = 0;
+        SGMB_ShardRange(n, ndev, g, &lo, &hi);
         return hi > lo ? SGMB_MatchBatch(c, lefts + lo, rights + lo, disps + lo, hi - lo) : SGMB_OK;
     });
 }
@@ -1056,67 +1182,120 @@ extern "C" int SGMB_TimeDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t
     return SGMB_OK;
 }
 
+// Per-kernel durations of one frame: events around every launch of the current pipeline (direct launches, no graph),
+// averaged over `iters` frames after `warmup` untimed ones.  Returns the number of kernels; names via SGMB_KernelName.
+extern "C" int SGMB_TimeKernels(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int warmup, int iters,
+                                float* kernel_ms, int capacity)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_TimeKernels: context is not configured");
+    if (!dL || !dR || !dOut || iters < 1 || warmup < 0 || !kernel_ms || capacity < 1) return fail(SGMB_E_ARG, "SGMB_TimeKernels: bad arguments");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    KernelTimer tm;
+    int rc = SGMB_OK, n = 0;
+    for (auto& e : tm.ev) if (cudaEventCreate(&e) != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaEventCreate failed");
+    std::vector<double> sum(kMaxTimedKernels, 0.0);
+    s.timer = &tm;
+    for (int it = -warmup; it < iters && rc == SGMB_OK; ++it) {
+        rc = enqueue_frame(c, s, dL, dR, dOut, false, nullptr);
+        if (rc == SGMB_OK && cudaStreamSynchronize(s.stream) != cudaSuccess) rc = fail(SGMB_E_CUDA, "SGMB_TimeKernels: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc != SGMB_OK || it < 0) continue;
+        n = tm.n;
+        for (int k = 0; k < n; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tm.ev[k], tm.ev[k + 1]);
+            sum[k] += ms;
+        }
+    }
+    s.timer = nullptr;
+    for (int k = 0; k < kMaxTimedKernels; ++k) c->timedName[k] = k < n ? tm.name[k] : nullptr;
+    for (auto& e : tm.ev) if (e) cudaEventDestroy(e);
+    if (rc != SGMB_OK) return rc;
+    for (int k = 0; k < n && k < capacity; ++k) kernel_ms[k] = (float)(sum[k] / iters);
+    return n;
+}
+
+extern "C" const char* SGMB_KernelName(SGMB_Context* c, int index)
+{
+    return (c && index >= 0 && index < kMaxTimedKernels && c->timedName[index]) ? c->timedName[index] : "";
+}
+
 // Enqueue `iters` frames back to back on slot 0 (device-resident input and output, no host synchronisation in
 // between) and time the whole region with CUDA events on that stream; optionally also every aggregation launch.
+// The frames are recorded into ONE CUDA graph (kernel nodes, the memsets and - when asked for - external event records
+// around every aggregation kernel) and replayed with a single launch: the launch-bound inner loop of a device-resident
+// batch.  `replays` > 1 launches the same graph that many times, each replay timed on its own (replay_ms[r]).
+static int run_device(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int iters, int replays,
+                      float* replay_ms, float* agg_ms)
+{
+    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_RunDevice: context is not configured");
+    if (!dL || !dR || !dOut || iters < 1 || replays < 1) return fail(SGMB_E_ARG, "SGMB_RunDevice: bad arguments");
+    if (int rc = ensure_device(c)) return rc;
+    Slot& s = c->slots[0];
+    std::vector<cudaEvent_t> ev(agg_ms ? 2 * (size_t)iters : 0, nullptr);
+    const cudaEvent_t keep0 = s.evAgg0, keep1 = s.evAgg1;
+    const bool useGraph = !getenv("SGM_B200_NO_GRAPH");
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool capturing = false;
+    auto enqueue_all = [&]() -> int {
+        for (int it = 0; it < iters; ++it) {
+            if (agg_ms) { s.evAgg0 = ev[2 * it]; s.evAgg1 = ev[2 * it + 1]; }
+            if (int rc = enqueue_frame(c, s, dL, dR, dOut, agg_ms != nullptr, nullptr)) return rc;
+        }
+        return SGMB_OK;
+    };
+    const int rc = [&]() -> int {
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        if (useGraph) {
+            CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+            capturing = c->capturing = true;
+            const int erc = enqueue_all();
+            c->capturing = false;
+            const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+            capturing = false;
+            if (erc) return erc;
+            if (e != cudaSuccess) return fail(SGMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            CU(cudaGraphInstantiate(&exec, graph, 0));
+            CU(cudaGraphUpload(exec, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+        }
+        for (int r = 0; r < replays; ++r) {
+            CU(cudaEventRecord(s.evStart, s.stream));
+            if (useGraph) CU(cudaGraphLaunch(exec, s.stream));
+            else if (int erc = enqueue_all()) return erc;
+            CU(cudaEventRecord(s.evStop, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
+            if (replay_ms) replay_ms[r] = c->lastMs;
+        }
+        if (agg_ms) for (int it = 0; it < iters; ++it) CU(cudaEventElapsedTime(&agg_ms[it], ev[2 * it], ev[2 * it + 1]));
+        return SGMB_OK;
+    }();
+    // every exit path: leave capture mode, restore the slot's own events, release what was created
+    if (capturing) { c->capturing = false; cudaGraph_t g = nullptr; cudaStreamEndCapture(s.stream, &g); if (g) cudaGraphDestroy(g); }
+    s.evAgg0 = keep0; s.evAgg1 = keep1;
+    if (rc != SGMB_OK) cudaStreamSynchronize(s.stream);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    return rc;
+}
+
 extern "C" int SGMB_RunDevice(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int iters,
                               float* total_ms, float* agg_ms /* [iters] or NULL */)
 {
-    if (!c || !c->configured) return fail(SGMB_E_STATE, "SGMB_RunDevice: context is not configured");
-    if (!dL || !dR || !dOut || iters < 1) return fail(SGMB_E_ARG, "SGMB_RunDevice: bad arguments");
-    if (int rc = ensure_device(c)) return rc;
-    Slot& s = c->slots[0];
-    std::vector<cudaEvent_t> ev;
-    if (agg_ms) {
-        ev.resize(2 * (size_t)iters);
-        for (auto& e : ev) CU(cudaEventCreate(&e));
-    }
-    cudaEvent_t keep0 = s.evAgg0, keep1 = s.evAgg1;
-    // The frames are recorded into ONE CUDA graph (kernel nodes, the side-buffer memset and - when asked for - external
-    // event records around every aggregation kernel) and replayed with a single launch: the launch-bound inner loop of
-    // a device-resident batch.  Pipelines with the in-place median are enqueued directly (its exchange epoch is a kernel
-    // argument that changes every frame).
-    const bool useGraph = !(c->pipeline & SGMB_PIPE_MEDIAN) && !getenv("SGM_B200_NO_GRAPH");
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    int rc = SGMB_OK;
-    if (useGraph) {
-        CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-        c->capturing = true;
-    } else {
-        CU(cudaEventRecord(s.evStart, s.stream));
-    }
-    for (int it = 0; it < iters && rc == SGMB_OK; ++it) {
-        if (agg_ms) { s.evAgg0 = ev[2 * it]; s.evAgg1 = ev[2 * it + 1]; }
-        rc = enqueue_frame(c, s, dL, dR, dOut, agg_ms != nullptr, nullptr);
-    }
-    s.evAgg0 = keep0; s.evAgg1 = keep1;
-    if (useGraph) {
-        c->capturing = false;
-        const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
-        if (rc == SGMB_OK && e != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        if (rc == SGMB_OK) {
-            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
-            if (e2 != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2));
-        }
-        if (rc == SGMB_OK) {
-            cudaGraphUpload(exec, s.stream);
-            cudaStreamSynchronize(s.stream);
-            cudaEventRecord(s.evStart, s.stream);
-            const cudaError_t e3 = cudaGraphLaunch(exec, s.stream);
-            if (e3 != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e3));
-        }
-    }
-    if (rc == SGMB_OK) {
-        CU(cudaEventRecord(s.evStop, s.stream));
-        CU(cudaStreamSynchronize(s.stream));
-        CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
-        if (total_ms) *total_ms = c->lastMs;
-        if (agg_ms) for (int it = 0; it < iters; ++it) CU(cudaEventElapsedTime(&agg_ms[it], ev[2 * it], ev[2 * it + 1]));
-    }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-    for (auto& e : ev) cudaEventDestroy(e);
+    float ms = 0.f;
+    const int rc = run_device(c, dL, dR, dOut, iters, 1, &ms, agg_ms);
+    if (rc == SGMB_OK && total_ms) *total_ms = ms;
     return rc;
+}
+
+extern "C" int SGMB_RunDeviceReplays(SGMB_Context* c, const uint8_t* dL, const uint8_t* dR, float* dOut, int iters, int replays,
+                                     float* replay_ms /* [replays] */, float* agg_ms /* [iters] of the last replay, or NULL */)
+{
+    if (!replay_ms) return fail(SGMB_E_ARG, "SGMB_RunDeviceReplays: bad arguments");
+    return run_device(c, dL, dR, dOut, iters, replays, replay_ms, agg_ms);
 }
 
 // ------------------------------------------------------------------------------------------------ reference API

@@ -256,28 +256,7 @@ def test_kitti_shape_c2_against_oracle(oracle):
                 assert v.mean() > 0.5 and (np.abs(got_final[v] - truth[v]) <= 0.5).mean() > 0.99
 
 
-@pytest.mark.parametrize("w,h,d,paths", [(2864, 1924, 256, 8), (3840, 2160, 256, 8)])
-def test_full_size_properties_c3_c5(w, h, d, paths):
-    """Configs C3 / C5 (too slow for the CPU oracle inside the GPU test budget): size-independent properties.
-    * a uniform shift s of random texture is recovered: valid pixels equal s to within 0.5 px;
-    * determinism: two runs are bit-identical;
-    * invalid pixels are exactly +inf, valid ones lie in (min_d, max_d - 1);
-    * every right-view-consistent pixel survives: the LR check can only remove pixels."""
-    opts = options(max_disparity=d, num_paths=paths)
-    left, right, truth = make_pair(w, h, d, seed=0xB200, texture="noise")
-    with sgm.Context(0) as c:
-        c.set_pipeline(sgm.PIPE_HOTPATH | sgm.PIPE_TAPS)
-        c.configure(w, h, to_sgm_option(opts))
-        a = c.match(left, right)
-        wta = c.stage("disp_left_wta")
-        b = c.match(left, right)
-    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    v = np.isfinite(a)
-    assert np.all(a[~v].view(np.uint32) == 0x7F800000)
-    assert v.mean() > 0.5
-    assert np.all((a[v] > 0) & (a[v] < d - 1))
-    assert (np.abs(a[v] - truth[v]) <= 0.5).mean() > 0.99
-    assert np.all(np.isfinite(wta[v])) and np.array_equal(a[v], wta[v])
+# Configs C3 / C5 at full size and all 256 pairs of C4: tests/test_full_size_gpu.py (fixtures from the compiled reference).
 
 
 # ---------------------------------------------------------------------------------------------- 9x7 census extension
