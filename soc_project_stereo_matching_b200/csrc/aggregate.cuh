@@ -34,6 +34,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <type_traits>
 #include "path_walker.h"
 
 namespace sgmb {
@@ -68,11 +69,13 @@ struct AggParams {
     int nIrregularWarps, nRegularWarps;
     int W, H, D, Dp, dmin;
     int wrapInterior;           // 1: a visit without out-of-image costs can still exceed 255 (largest census cost + largest P2 > 255)
+    uint32_t zero;              // always 0, but only known at run time (see aggregate_columns_ilp::row_costs)
     uint32_t p1x2;              // min(P1, 256) in both 16-bit fields
     uint32_t p2x2[256];         // min(256, max(P1, P2_init/(delta+1))) in both fields, indexed by |g - gPrev|
 };
 
 constexpr int kAggWarpsPerBlock = 4;
+constexpr int kAggIlpColumns = 4;       // paths per warp of the column-ILP layout (aggregate_columns_ilp)
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 template <int NR, typename DT>
@@ -432,8 +435,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 // ------------------------------------------------------------------------------------------------ vertical / diagonal paths
 // A regular vertical or diagonal path follows a column or the toroidal diagonal, so its position is updated
 // with a constant stride (plus one column wrap for diagonals); 32/LPP paths of one direction share a warp and
-// every lane owns 2*NR disparities.  The loads of visit s+1 are issued before the dependent chain of visit s
-// (two input buffers, loop unrolled by two).
+// every lane owns 2*NR disparities.  The loads of visit s+1 are issued right after the costs of visit s have been formed.
 template <int NR, int LPP, bool DIAG, typename DT, bool PAD>
 __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const WarpWork job, int lane)
 {
@@ -483,13 +485,31 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
         if (border) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
         else pack_cost<NR, false, DT>(in, 0, C);
     };
-    auto visit = [&](const StepInput<NR, DT>& in, uint32_t p, int tc) {
-        const bool slow = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
-        if (slow) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
-        else pack_cost<NR, false, DT>(in, 0, C);
-        int dg = (int)in.g - (int)gPrev;
+    // ONE input buffer: the loads of visit s + 1 are issued right after the costs of visit s have been formed (the last use
+    // of its inputs) and fly during the dependent chain of visit s.  ptxas tracks all loads of the loop with one hardware
+    // scoreboard, so a request issued between a load and its first use is waited for as well: with three buffers fetched
+    // "two visits ahead" (round 1) the first use of one buffer per three visits waited a full memory latency - 42 % of the
+    // stall samples of a lone warp, 1.5 stalled warps per issued instruction at full load (ncu r2_g, r1_j).
+    StepInput<NR, DT> in;
+    uint32_t qn = pos;
+    int tn = tcol;
+    load_step<NR, DT>(P, pos, sub, in);
+    // ---- first pixel: L = C (SemiGlobalMatching.c:266-275)
+    cost(in, tn);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
+    gPrev = in.g;
+    posPrev = qn;
+    if (1 < len) { advance(); qn = pos; tn = tcol; load_step<NR, DT>(P, pos, sub, in); }
+    minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
+
+    for (int s = 1; s < len; ++s) {
+        cost(in, tn);                                   // waits for the loads of visit s
+        const uint32_t g = in.g, p = qn;
+        if (s + 1 < len) { advance(); qn = pos; tn = tcol; load_step<NR, DT>(P, pos, sub, in); }
+        int dg = (int)g - (int)gPrev;
         dg = dg < 0 ? -dg : dg;
-        gPrev = in.g;
+        gPrev = g;
         const uint32_t p2x2 = P.p2x2[dg];
         const uint32_t negmin = __vneg2(minx2);
         uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1, LPP);
@@ -501,45 +521,240 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
         dp_step<NR, true>(L, C, padm, up, dn, p1x2, p2x2, negmin);
         minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
         posPrev = p;
-    };
-
-    // Loads run two visits ahead of the dependent chain (three input buffers, loop unrolled by three): with ~4
-    // warps per scheduler a visit takes several hundred cycles, so two visits cover an L2 miss.
-    StepInput<NR, DT> in0, in1, in2;
-    uint32_t q0 = pos, q1 = 0, q2 = 0;
-    int t0 = tcol, t1 = 0, t2 = 0;
-    load_step<NR, DT>(P, pos, sub, in0);
-    if (1 < len) { advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1); }
-    if (2 < len) { advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2); }
-    // ---- first pixel: L = C (SemiGlobalMatching.c:266-275)
-    cost(in0, t0);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
-    minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
-    gPrev = in0.g;
-    posPrev = q0;
-
-    int s = 1;      // next visit to process: its inputs are in in1, those of visit s+1 in in2
-    // main loop: three visits per iteration with the buffers rotating statically (no register moves) and every
-    // prefetch unconditional: the last one fetches visit s+4 <= len-1
-    for (; s + 5 <= len; s += 3) {
-        advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0);
-        visit(in1, q1, t1);
-        advance(); q1 = pos; t1 = tcol; load_step<NR, DT>(P, pos, sub, in1);
-        visit(in2, q2, t2);
-        advance(); q2 = pos; t2 = tcol; load_step<NR, DT>(P, pos, sub, in2);
-        visit(in0, q0, t0);
-    }
-    // tail: at most four visits, one at a time
-    while (s < len) {
-        const bool more = s + 2 < len;
-        if (more) { advance(); q0 = pos; t0 = tcol; load_step<NR, DT>(P, pos, sub, in0); }
-        visit(in1, q1, t1);
-        ++s;
-        in1 = in2; q1 = q2; t1 = t2;
-        if (more) { in2 = in0; q2 = q0; t2 = t0; }
     }
     if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);
+}
+
+// ------------------------------------------------------------------------------------------------ vertical / diagonal paths, column-ILP layout
+// The layout above runs ONE dependent chain per warp (four paths in lock step in four lane groups): shuffle -> DPX
+// min/add -> lane minimum -> three-round butterfly -> next visit, and a lone warp of it issues one instruction every
+// ~6 cycles.  With only ~3.8 warps per scheduler at C2 that latency is the kernel's bound.  Here
+// a warp still owns NCOL paths of one direction - paths i .. i+NCOL-1 sit on ADJACENT image columns at every step, also
+// on the toroidal diagonals - but as NCOL INDEPENDENT chains in the same lanes: lane s holds, for every column, the
+// 2*NRC disparity indices [2*NRC*s, 2*NRC*(s+1)), so that
+//   * the instruction streams of the NCOL columns interleave (NCOL-fold instruction-level parallelism per warp);
+//   * the path minimum is one warp-wide REDUX per column instead of a shuffle butterfly;
+//   * adjacent columns share all but one descriptor of their right-census windows: a lane fetches 2*NRC + NCOL - 1
+//     descriptors per visit instead of NCOL * 2*NRC (7 instead of 16 at D = 128), all from ONE shifted copy of the
+//     right census with aligned 128-bit loads (L1 wavefronts per visit: ~8 instead of ~64);
+//   * register r of a column pairs the disparity indices (r, r + NRC) of the lane ("stride pairing"), so Lp[d-1] / Lp[d+1]
+//     of a register are simply the neighbouring registers; only the two registers at the lane's edges need a PRMT with
+//     the value shuffled in from the neighbouring lane.
+// Rows on which the NCOL columns are not contiguous in memory (the group straddles the wrap of a toroidal diagonal:
+// at most NCOL-1 rows per warp; or a group with fewer than NCOL paths, whose spare columns shadow the last path) take
+// per-column loads without prefetch; the DP itself is the same code.
+template <int NRC>
+__device__ __forceinline__ void store_column(uint8_t* dst, const uint32_t (&L)[NRC])
+{
+    // natural byte order k0 .. k(2*NRC-1) from registers (k_r, k_{r+NRC})
+    if constexpr (NRC == 1) {
+        __stcs(reinterpret_cast<unsigned short*>(dst), (unsigned short)__byte_perm(L[0], 0, 0x4420));
+    } else if constexpr (NRC == 2) {
+        __stcs(reinterpret_cast<uint32_t*>(dst), __byte_perm(L[0], L[1], 0x6240));
+    } else {
+        static_assert(NRC <= 4, "NRC");
+        const uint32_t a = __byte_perm(L[0], L[1], 0x6240);        // k0 k1 k4 k5
+        const uint32_t b = __byte_perm(L[NRC - 2], L[NRC - 1], 0x6240);   // k2 k3 k6 k7
+        __stcs(reinterpret_cast<uint2*>(dst), make_uint2(__byte_perm(a, b, 0x5410), __byte_perm(a, b, 0x7632)));
+    }
+}
+
+template <int NRC, int NCOL, bool DIAG, bool PAD>
+__device__ __forceinline__ void aggregate_columns_ilp(const AggParams& P, const WarpWork job, int lane)
+{
+    static_assert(NRC == 1 || NRC == 2 || NRC == 4, "NRC");
+    constexpr int DPL = 2 * NRC;                        // disparity indices per lane and column
+    constexpr int NW = DPL + NCOL - 1;                  // descriptors of the shared window
+    constexpr int NVW = (NW + 3) / 4;                   // 128-bit loads of the shared window
+    constexpr unsigned FULL = 0xffffffffu;
+    const Dir dir = direction(job.dir);
+    const bool fwd = dir.dy > 0;
+    const int W = P.W, H = P.H, len = H;
+    const int nact = (int)job.count;                    // paths really owned; spare columns shadow the last one
+    const bool fullGroup = nact == NCOL;
+
+    uint32_t padm[NRC];
+#pragma unroll
+    for (int r = 0; r < NRC; ++r) {
+        const int i0 = DPL * lane + r, i1 = i0 + NRC;
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
+    }
+    const int dbase = P.dmin + DPL * lane;              // absolute disparity of the lane's first index
+    const int dlast = P.dmin + DPL * 32 - 1;            // largest absolute disparity any lane may hold
+    const bool stores = PAD ? (DPL * lane < P.Dp) : true;
+    uint8_t* const planeLane = P.planes + (size_t)job.dir * P.planeStride + DPL * lane;
+    const uint32_t p1x2 = P.p1x2;
+    const uint2* const pixL = static_cast<const uint2*>(P.pixL);
+    const uint32_t* const cR4 = static_cast<const uint32_t*>(P.censusR4);
+    const uint32_t upMask = lane == 0 ? 0x00FF00FFu : 0u, dnMask = lane == 31 ? 0x00FF00FFu : 0u;   // Lp[-1] = Lp[D] = 255
+
+    // position of column 0 (path job.firstPath) at the current step
+    uint32_t pos0 = fwd ? (uint32_t)job.firstPath : (uint32_t)((H - 1) * W + job.firstPath);
+    int tcol0 = job.firstPath;
+    const uint32_t dpos = (uint32_t)(dir.dy * W + dir.dx);
+    const int dcol = dir.dx;
+    auto advance = [&]() {
+        pos0 += dpos;
+        if (DIAG) {
+            tcol0 += dcol;
+            if (tcol0 >= W) { tcol0 -= W; pos0 -= (uint32_t)W; }
+            if (tcol0 < 0)  { tcol0 += W; pos0 += (uint32_t)W; }
+        }
+    };
+    // column c of the group at the row where column 0 is at (p0, t0): same row, column (t0 + c) mod W
+    auto column_at = [&](uint32_t p0, int t0, int c, uint32_t& pc, int& tc) {
+        const int ce = c < nact ? c : nact - 1;
+        tc = t0 + ce; pc = p0 + (uint32_t)ce;
+        if (tc >= W) { tc -= W; pc -= (uint32_t)W; }
+    };
+
+    struct RowIn {                // inputs of one row when its columns are contiguous in memory
+        uint32_t v[4 * NVW];      // v[j] = cR[pos0 - dmin - DPL*lane - (DPL-1) + j]
+        uint32_t cl[NCOL], g[NCOL];
+        uint32_t pos0; int tcol0; bool contig;
+    };
+    auto prefetch = [&](RowIn& in) {
+        in.pos0 = pos0; in.tcol0 = tcol0;
+        in.contig = fullGroup && (!DIAG || tcol0 + NCOL - 1 < W);
+        if (!in.contig) return;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const uint2 px = __ldg(pixL + pos0 + c);
+            in.cl[c] = px.x; in.g[c] = px.y;
+        }
+        const uint32_t y0 = pos0 - (uint32_t)(P.dmin + DPL * lane + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
+        const uint32_t al = (y0 + 3u) & ~3u;
+        const uint4* src = reinterpret_cast<const uint4*>(cR4 + ((al - y0) * P.copyStride + al));
+#pragma unroll
+        for (int j = 0; j < NVW; ++j) {
+            const uint4 t = __ldg(src + j);
+            in.v[4 * j + 0] = t.x; in.v[4 * j + 1] = t.y; in.v[4 * j + 2] = t.z; in.v[4 * j + 3] = t.w;
+        }
+    };
+
+    uint32_t L[NCOL][NRC], C[NCOL][NRC], minx2[NCOL], gPrev[NCOL], gCur[NCOL];
+    uint32_t posc[NCOL];
+
+    // matching costs of the row (SemiGlobalMatching.c:170-177), registers paired (k = r, k = r + NRC).  Returns whether
+    // some field may hold the out-of-image cost 127 (then C + penalty can exceed 255 and the uint8 wrap matters).
+    auto row_costs = [&](const RowIn& in) -> bool {
+        if (in.contig) {
+            // The window is loaded in whole 128-bit vectors, so its last 4*NVW - NW elements are never read.  Without this
+            // (empty) use ptxas treats their registers as free and reuses them as scratch while the load is still in
+            // flight; the write-after-write hazard then waits for the load right behind its issue - the full memory latency
+            // on every row (50 % of the stall samples of a lone warp, ncu r2_g).
+            uint32_t keep = 0;
+#pragma unroll
+            for (int j = NW; j < 4 * NVW; ++j) keep |= in.v[j];
+            keep &= P.zero;                              // a run-time 0 that the compiler cannot fold: one LOP3 per row
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) { posc[c] = in.pos0 + c + keep; gCur[c] = in.g[c]; }
+            if (in.tcol0 < dlast) {                      // warp-uniform: some right column x - d may be negative
+#pragma unroll
+                for (int c = 0; c < NCOL; ++c) {
+                    const int nvalid = in.tcol0 + c - dbase + 1;
+#pragma unroll
+                    for (int r = 0; r < NRC; ++r) {
+                        const uint32_t c0 = (r < nvalid) ? (uint32_t)__popc(in.cl[c] ^ in.v[DPL - 1 + c - r]) : 127u;
+                        const uint32_t c1 = (r + NRC < nvalid) ? (uint32_t)__popc(in.cl[c] ^ in.v[DPL - 1 + c - r - NRC]) : 127u;
+                        C[c][r] = c1 * 65536u + c0;
+                    }
+                }
+                return true;
+            }
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+                for (int r = 0; r < NRC; ++r)
+                    C[c][r] = (uint32_t)__popc(in.cl[c] ^ in.v[DPL - 1 + c - r - NRC]) * 65536u + (uint32_t)__popc(in.cl[c] ^ in.v[DPL - 1 + c - r]);
+            return false;
+        }
+        // per-column loads, no prefetch (rare: see the header comment)
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            uint32_t pc; int tc;
+            column_at(in.pos0, in.tcol0, c, pc, tc);
+            StepInput<NRC, uint32_t> one;
+            load_step<NRC, uint32_t>(P, pc, lane, one);
+            posc[c] = pc;
+            gCur[c] = one.g;
+            const int nvalid = tc - dbase + 1;
+#pragma unroll
+            for (int r = 0; r < NRC; ++r) {
+                const uint32_t c0 = (r < nvalid) ? (uint32_t)__popc(one.cl ^ one.v[DPL - 1 - r]) : 127u;
+                const uint32_t c1 = (r + NRC < nvalid) ? (uint32_t)__popc(one.cl ^ one.v[DPL - 1 - r - NRC]) : 127u;
+                C[c][r] = c1 * 65536u + c0;
+            }
+        }
+        return true;
+    };
+    auto lane_min = [&](const uint32_t (&Lc)[NRC]) {
+        uint32_t m = Lc[0];
+#pragma unroll
+        for (int r = 1; r < NRC; ++r) m = __vminu2(m, Lc[r]);
+        return __vminu2(m, __byte_perm(m, 0, 0x1032));                        // both fields = minimum of the lane
+    };
+    const uint32_t Dp = PAD ? (uint32_t)P.Dp : (uint32_t)(64 * NRC);       // bytes per pixel of a plane; a constant without padding
+    auto store_row = [&](bool contig) {
+        if (!stores) return;
+        if (contig) {
+            uint8_t* dst = planeLane + (size_t)posc[0] * Dp;
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) store_column<NRC>(dst + c * Dp, L[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) store_column<NRC>(planeLane + (size_t)posc[c] * Dp, L[c]);
+        }
+    };
+
+    // ONE input buffer: the loads of row s + 1 are issued right after the last use of row s' inputs (its costs) and fly
+    // during the DP of row s.  No load is ever issued between a load and its first use: ptxas tracks all loads of the loop
+    // with one hardware scoreboard, so a request issued in between would be waited for as well (with a second buffer
+    // fetched "one row ahead" the wait before every row's costs took 19 % of the kernel's stall samples, ncu r2_c).
+    RowIn in;
+    prefetch(in);
+    // ---- first pixel of every path: L = C (SemiGlobalMatching.c:266-275)
+    bool contig = in.contig;
+    (void)row_costs(in);
+    if (1 < len) { advance(); prefetch(in); }
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) L[c][r] = C[c][r] | padm[r];
+        minx2[c] = __reduce_min_sync(FULL, lane_min(L[c]));
+        gPrev[c] = gCur[c];
+    }
+    store_row(contig);
+
+    for (int s = 1; s < len; ++s) {
+        contig = in.contig;
+        (void)row_costs(in);
+        if (s + 1 < len) { advance(); prefetch(in); }
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            int dg = (int)gCur[c] - (int)gPrev[c];
+            dg = dg < 0 ? -dg : dg;
+            gPrev[c] = gCur[c];
+            const uint32_t p2x2 = P.p2x2[dg];
+            const uint32_t negmin = __vneg2(minx2[c]);
+            const uint32_t up = __shfl_up_sync(FULL, L[c][NRC - 1], 1) | upMask;     // fields <= 255: OR with 0x00FF00FF == 255
+            const uint32_t dn = __shfl_down_sync(FULL, L[c][0], 1) | dnMask;
+            uint32_t N[NRC];
+#pragma unroll
+            for (int r = 0; r < NRC; ++r) {
+                const uint32_t lm1 = (r == 0) ? __byte_perm(up, L[c][NRC - 1], 0x5432) : L[c][r - 1];        // Lp[d-1] of both fields
+                const uint32_t lp1 = (r == NRC - 1) ? __byte_perm(L[c][0], dn, 0x5432) : L[c][r + 1];        // Lp[d+1]
+                uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[c][r]);
+                t = __viaddmin_u16x2(lp1, p1x2, t);
+                t = __viaddmin_u16x2(t, negmin, p2x2);                         // min(. - minPrev, P2') in [0, 255]
+                N[r] = ((C[c][r] + t) & 0x00FF00FFu) | padm[r];                // (uint8)(C + m - minPrev); fields <= 127 + 255: no carry
+            }
+#pragma unroll
+            for (int r = 0; r < NRC; ++r) L[c][r] = N[r];
+            minx2[c] = __reduce_min_sync(FULL, lane_min(L[c]));
+        }
+        store_row(contig);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ irregular paths
@@ -563,55 +778,64 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
     PathWalker wk;
     wk.start(P.W, P.H, dir.dx, dir.dy, job.firstPath);
     const int len = wk.length();
-    uint32_t L[NR], C[NR];
+    uint32_t L[NR];
     uint32_t minx2 = 0x00FF00FFu, gPrev = 0;
     bool first = true;
 
-    // The walk does not depend on data, so the inputs of later visits are fetched while the current one is
-    // processed: a ring of kAhead+1 input sets (these four warps run alone on their schedulers, nothing else
-    // hides their memory latency).
-    constexpr int kAhead = 3;
-    StepInput<NR, DT> ring[kAhead + 1];
-    int posR[kAhead + 1], tcR[kAhead + 1], eR[kAhead + 1];
-    bool inR[kAhead + 1];
+    // The walk does not depend on data and neither do the matching costs, so the path is processed in blocks of kBlock
+    // visits: wait for the block's inputs, form the costs of all its visits, issue the loads of the NEXT block, then run
+    // the kBlock dependent DP steps while those loads fly.  No load is issued between a load and its first use (ptxas
+    // tracks them with one scoreboard), and a whole block of DP steps covers the memory latency: these four warps run alone
+    // on their schedulers, and with one visit fetched per visit processed (round 1) they took 237 us at C2 - as long as
+    // all regular paths together (ncu r2_f).
+    constexpr int kBlock = 4;
+    StepInput<NR, DT> ring[kBlock];
+    int tcR[kBlock], eR[kBlock];
+    bool inR[kBlock];
     auto fetch = [&](int slot) {
-        posR[slot] = wk.pos; tcR[slot] = wk.tcol; inR[slot] = wk.inside(); eR[slot] = -1;
+        tcR[slot] = wk.tcol; inR[slot] = wk.inside(); eR[slot] = -1;
         if (inR[slot]) { load_step<NR, DT>(P, (uint32_t)wk.pos, lane, ring[slot]); eR[slot] = __ldg(P.entryOf + wk.pos); }
-    };
-    auto process = [&](int slot) {
-        if (!inR[slot]) return;                   // the reference's out-of-bounds visit: skipped (warp-uniform)
-        pack_cost<NR, true, DT>(ring[slot], tcR[slot] - dbase + 1, C);
-        if (first) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) L[r] = C[r] | padm[r];
-            first = false;
-        } else {
-            int dg = (int)ring[slot].g - (int)gPrev;
-            dg = dg < 0 ? -dg : dg;
-            uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
-            uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
-            if (lane == 0) up = 0x00FF00FFu;
-            if (lane == 31) dn = 0x00FF00FFu;
-            dp_step<NR>(L, C, padm, up, dn, P.p1x2, P.p2x2[dg], __vneg2(minx2));
-        }
-        minx2 = group_min_x2<32>(lane_min_x2<NR>(L));
-        gPrev = ring[slot].g;
-        if (eR[slot] >= 0 && lane_stores) {
-            uint32_t* dst = P.side + ((size_t)eR[slot] * P.Dp + DPL * lane) / 2;
-#pragma unroll
-            for (int r = 0; r < NR; ++r) atomicAdd(dst + r, L[r] & ~padm[r]);
-        }
     };
     int fetched = 0;                              // visits whose loads have been issued
 #pragma unroll
-    for (int k = 0; k <= kAhead; ++k)
+    for (int k = 0; k < kBlock; ++k)
         if (fetched < len) { if (fetched) wk.advance(); fetch(k); ++fetched; }
-    for (int s = 0; s < len; s += kAhead + 1) {
+    for (int s = 0; s < len; s += kBlock) {
+        uint32_t Cb[kBlock][NR], gB[kBlock];
+        int eB[kBlock];
+        bool inB[kBlock];
 #pragma unroll
-        for (int k = 0; k <= kAhead; ++k) {
-            if (s + k < len) {
-                process(k);
-                if (fetched < len) { wk.advance(); fetch(k); ++fetched; }
+        for (int k = 0; k < kBlock; ++k) {
+            inB[k] = (s + k < len) && inR[k];     // the reference's out-of-bounds visit is skipped (warp-uniform)
+            eB[k] = eR[k];
+            gB[k] = ring[k].g;
+            if (inB[k]) pack_cost<NR, true, DT>(ring[k], tcR[k] - dbase + 1, Cb[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kBlock; ++k)
+            if (fetched < len) { wk.advance(); fetch(k); ++fetched; }
+#pragma unroll
+        for (int k = 0; k < kBlock; ++k) {
+            if (!inB[k]) continue;
+            if (first) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) L[r] = Cb[k][r] | padm[r];
+                first = false;
+            } else {
+                int dg = (int)gB[k] - (int)gPrev;
+                dg = dg < 0 ? -dg : dg;
+                uint32_t up = __shfl_up_sync(FULL, L[NR - 1], 1);
+                uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
+                if (lane == 0) up = 0x00FF00FFu;
+                if (lane == 31) dn = 0x00FF00FFu;
+                dp_step<NR>(L, Cb[k], padm, up, dn, P.p1x2, P.p2x2[dg], __vneg2(minx2));
+            }
+            minx2 = group_min_x2<32>(lane_min_x2<NR>(L));
+            gPrev = gB[k];
+            if (eB[k] >= 0 && lane_stores) {
+                uint32_t* dst = P.side + ((size_t)eB[k] * P.Dp + DPL * lane) / 2;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) atomicAdd(dst + r, L[r] & ~padm[r]);
             }
         }
     }
@@ -635,6 +859,23 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
     else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD>(P, job, lane);
     else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT, PAD>(P, job, lane);
     else                          aggregate_column_like<NRV, LPPV, true, DT, PAD>(P, job, lane);
+}
+
+// Same job list, vertical / diagonal paths in the column-ILP layout (32-bit descriptors only):
+// NRH/LPPH horizontal layout, NRC registers per column (D <= 64 * NRC), NCOL columns per warp, NRI irregular layout.
+template <int NRH, int LPPH, int NRC, int NCOL, int NRI, bool PAD>
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+sgm_aggregate_paths_ilp(const __grid_constant__ AggParams P)
+{
+    const int widx = blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
+    const WarpWork job = P.work[widx];
+    if (widx < P.nIrregularWarps) aggregate_irregular<NRI, uint32_t, PAD>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, uint32_t, PAD>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, uint32_t, PAD>(P, job, lane);
+    else if (job.dir < 4)         aggregate_columns_ilp<NRC, NCOL, false, PAD>(P, job, lane);
+    else                          aggregate_columns_ilp<NRC, NCOL, true, PAD>(P, job, lane);
 }
 
 }  // namespace sgmb

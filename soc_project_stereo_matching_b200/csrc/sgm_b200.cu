@@ -115,6 +115,7 @@ struct SGMB_Context {
     int lppV = 8;                 // lanes per path of the vertical / diagonal directions
     int lppH = 16;                // lanes per path of the horizontal directions
     int altLayout = 0;            // SGM_B200_DEBUG_LAYOUT: alternative kernel layouts for experiments
+    bool ilp = false;             // vertical / diagonal paths in the column-ILP layout (32-bit descriptors)
     int32_t* entryOf = nullptr;
     int nEntries = 0, nIrregular = 0;
     uint32_t p2x2[256] = {};
@@ -343,6 +344,11 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->altLayout = getenv("SGM_B200_DEBUG_LAYOUT") ? atoi(getenv("SGM_B200_DEBUG_LAYOUT")) : 0;   // experiments only
     if (c->altLayout == 1 && c->descBytes == 4 && c->NR == 2) c->lppV = 16;
     c->lppH = 16;
+    // 32-bit descriptors (the reference's census): vertical / diagonal paths in the column-ILP layout (aggregate.cuh), a
+    // warp owning kAggIlpColumns adjacent paths with all 32 lanes on every one of them, and one horizontal path per warp.
+    // SGM_B200_DEBUG_LAYOUT=3 selects the lane-group layout of round 1 for comparison, 4 keeps its horizontal layout only.
+    c->ilp = c->descBytes == 4 && c->altLayout != 3 && c->altLayout != 1 && c->altLayout != 2;
+    if (c->ilp) { c->lppV = 32 / kAggIlpColumns; c->lppH = c->altLayout == 4 ? 16 : 32; }
     const int perWarpV = 32 / c->lppV, perWarpH = 32 / c->lppH;
     std::vector<WarpWork> irregular, regular;
     std::vector<int32_t> entryOf(c->N, -1);
@@ -355,8 +361,15 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         size_t i = 0;
         while (i < paths.size()) {                 // consecutive path indices only, so a warp's groups are first..first+count-1
             size_t j = i + 1;
-            while (j < paths.size() && (int)(j - i) < perWarp && paths[j] == paths[j - 1] + 1) ++j;
-            regular.push_back(WarpWork{paths[i], (uint8_t)d, (uint8_t)(j - i), 0});
+            while (j < paths.size() && paths[j] == paths[j - 1] + 1) ++j;     // [i, j): a run of consecutive paths
+            const size_t run = j - i;
+            for (size_t k = 0; k < run; k += perWarp) {
+                size_t n = std::min<size_t>(perWarp, run - k), first = i + k;
+                // column-ILP layout: a warp whose columns are not all real paths loses its prefetched fast path, so the last
+                // group of a run is moved back to overlap its predecessor (both write identical bytes to the shared paths)
+                if (c->ilp && d >= 2 && n < (size_t)perWarp && run >= (size_t)perWarp) { first = j - perWarp; n = perWarp; }
+                regular.push_back(WarpWork{paths[first], (uint8_t)d, (uint8_t)n, 0});
+            }
             i = j;
         }
     };
@@ -533,7 +546,22 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         if (pad) sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, true><<<blocks, threads, 0, s.stream>>>(p);  \
         else     sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, false><<<blocks, threads, 0, s.stream>>>(p); \
     } while (0)
-        if (c->descBytes == 4) {
+#define SGM_ILP_LAUNCH(NRH, LPPH, NRC, NRI)                                                                                 \
+    do {                                                                                                                   \
+        if (pad) sgm_aggregate_paths_ilp<NRH, LPPH, NRC, kAggIlpColumns, NRI, true><<<blocks, threads, 0, s.stream>>>(p);    \
+        else     sgm_aggregate_paths_ilp<NRH, LPPH, NRC, kAggIlpColumns, NRI, false><<<blocks, threads, 0, s.stream>>>(p);   \
+    } while (0)
+        if (c->ilp) {
+            if (c->lppH == 32) {
+                if (c->NR == 1)      SGM_ILP_LAUNCH(1, 32, 1, 1);
+                else if (c->NR == 2) SGM_ILP_LAUNCH(2, 32, 2, 2);
+                else                 SGM_ILP_LAUNCH(4, 32, 4, 4);
+            } else {
+                if (c->NR == 1)      SGM_ILP_LAUNCH(2, 16, 1, 1);
+                else if (c->NR == 2) SGM_ILP_LAUNCH(4, 16, 2, 2);
+                else                 SGM_ILP_LAUNCH(8, 16, 4, 4);
+            }
+        } else if (c->descBytes == 4) {
             if (c->NR == 1)                           SGM_AGG_LAUNCH(2, 16, 4, 8, 1, uint32_t);
             else if (c->NR == 2 && c->altLayout == 1) SGM_AGG_LAUNCH(4, 16, 4, 16, 2, uint32_t);
             else if (c->NR == 2)                      SGM_AGG_LAUNCH(4, 16, 8, 8, 2, uint32_t);
@@ -544,6 +572,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
             else                 SGM_AGG_LAUNCH(8, 16, 8, 16, 4, desc64_t);
         }
 #undef SGM_AGG_LAUNCH
+#undef SGM_ILP_LAUNCH
         if (timeAgg) CU(cudaEventRecordWithFlags(s.evAgg1, s.stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ++nk;
         if (int rc = mark("sgm_aggregate_paths")) return rc;
