@@ -34,7 +34,6 @@
 #pragma once
 
 #include <stdint.h>
-#include <type_traits>
 #include "path_walker.h"
 
 namespace sgmb {
@@ -55,10 +54,9 @@ __device__ __forceinline__ uint32_t desc_popc(desc64_t x) { return (uint32_t)__p
 struct AggParams {
     const uint8_t* img;         // left image [N]
     const void* censusL;        // DT [N]
-    const void* pixL;           // 16 bytes per pixel.  32-bit descriptors: uint4 {P2' of directions 0..3, descriptor, P2' of
-                                // directions 4..7, descriptor} - one 64-bit half is all a visit of the column-ring layout needs
-                                // besides its right-census window (census.cuh direction_penalties); 64-bit descriptors:
-                                // uint4 {lo, hi, grey, 0}, fetched with one vector load (load_step)
+    const void* pixL;           // {left descriptor, grey value} per pixel - uint2 for 32-bit descriptors, uint4 {lo, hi, grey, 0} for
+                                // 64-bit ones: what a column visit needs besides its right-census window, fetched with ONE vector
+                                // load (see load_step)
     const void* censusR4;       // DT [16 / sizeof(DT)][copyStride], see census.cuh
     uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
@@ -70,15 +68,11 @@ struct AggParams {
     int nIrregularWarps, nRegularWarps;
     int W, H, D, Dp, dmin;
     int wrapInterior;           // 1: a visit without out-of-image costs can still exceed 255 (largest census cost + largest P2 > 255)
-    uint32_t k65536;            // 65536, but only known at run time: c1 * k65536 + c0 stays ONE multiply-add on the FMA pipe instead
-                                // of a shift and an OR on the (busier) ALU pipe
     uint32_t p1x2;              // min(P1, 256) in both 16-bit fields
     uint32_t p2x2[256];         // min(256, max(P1, P2_init/(delta+1))) in both fields, indexed by |g - gPrev|
 };
 
 constexpr int kAggWarpsPerBlock = 4;
-// paths per warp of the column-ring layout (aggregate_columns_ring) for NRC registers per column
-constexpr int agg_ring_columns(int nrc) { return nrc == 2 ? 8 : 4; }
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 template <int NR, typename DT>
@@ -108,8 +102,8 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
         // wait (0.288 ms), reloading a buffer inside its consuming visit three visits ahead (0.284 ms), staging through
         // shared memory with cp.async (0.409 ms: the L1 data pipe, already the busiest unit, then carries every
         // window three times); this version: 0.282 ms at C2.
-        in.cl = __ldg(static_cast<const uint32_t*>(P.pixL) + 4 * (size_t)pos + 1);   // record {P2' 0..3, descriptor, P2' 4..7, descriptor}
-        in.g = __ldg(P.img + pos);
+        const uint2 px = __ldg(static_cast<const uint2*>(P.pixL) + pos);
+        in.cl = px.x; in.g = px.y;
     } else {
         const uint4 px = __ldg(static_cast<const uint4*>(P.pixL) + pos);
         in.cl = ((desc64_t)px.y << 32) | px.x; in.g = px.z;
@@ -548,264 +542,6 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
     if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);
 }
 
-// ------------------------------------------------------------------------------------------------ vertical / diagonal paths, column-ring layout
-// The lane-group layout above runs ONE dependent chain per warp (four paths in lock step in four lane groups) and every lane
-// group fetches its own 16-descriptor window: the kernel was bound by the L1 data pipe (83 %) and by the latency of its
-// loads, which ptxas tracks with a single scoreboard.  Here a warp owns NCOL paths of one direction
-// - paths i .. i+NCOL-1 sit on ADJACENT image columns at every step, also on the toroidal diagonals - as NCOL INDEPENDENT
-// chains in the same lanes: lane s holds, for every column, the 2*NRC disparity indices [2*NRC*s, 2*NRC*(s+1)).
-//   * The instruction streams of the NCOL columns interleave (instruction-level parallelism inside the warp), the path
-//     minimum is one warp-wide REDUX per column instead of a shuffle butterfly.
-//   * The right-census descriptors the whole warp needs for a row are ONE contiguous span of 31*2*NRC + 2*NRC + NCOL - 1
-//     elements (135 at D = 128, NCOL = 8: adjacent lanes and adjacent columns share all but a few descriptors).  The span
-//     and the NCOL pixel records are copied global -> shared with cp.async (16 bytes per lane, two instructions per row)
-//     into a ring of kRingRows rows per warp, several rows ahead of their use; the lanes then read their windows with
-//     128-bit shared-memory loads.  No register is the destination of a global load, so neither the single load
-//     scoreboard nor the reuse of dead destination registers (write-after-write waits, ncu r2_g) can expose the memory
-//     latency, and the L1 data pipe carries ~0.7 KB per row instead of ~4 KB per four paths.
-//   * Register r of a column pairs the disparity indices (r, r + NRC) of the lane ("stride pairing"), so Lp[d-1] / Lp[d+1]
-//     of a register are simply the neighbouring registers; only the two registers at the lane's edges need a PRMT with
-//     the value shuffled in from the neighbouring lane.
-//   * The adaptive penalty P2' comes as one byte per direction from the pixel record (formed once per pixel by the census
-//     kernel), so the visit needs no grey value, no table lookup and no previous-grey state.
-// Rows on which the NCOL columns are not contiguous in memory (the group straddles the wrap of a toroidal diagonal: at
-// most NCOL-1 rows per warp; or a group with fewer than NCOL paths, whose spare columns shadow the last path) take
-// per-column loads without prefetch; the DP itself is the same code.
-constexpr int kRingRows = 4;            // rows in flight per warp
-
-template <int NRC, int NCOL>
-struct ColumnRing {
-    static constexpr int DPL = 2 * NRC;                        // disparity indices per lane and column
-    static constexpr int NW = DPL + NCOL - 1;                  // descriptors one lane reads per row
-    static constexpr int SPAN = 31 * DPL + NW;                 // descriptors all lanes read together
-    static constexpr int WCH = (SPAN + 3) / 4;                 // 16-byte chunks of that span
-    static constexpr int CHUNKS = WCH + NCOL;                  // + one chunk (pixel record) per column
-    static constexpr int COPIES = (CHUNKS + 31) / 32;          // cp.async instructions per row (one chunk per lane each)
-    static constexpr int STAGE_BYTES = CHUNKS * 16;
-    static constexpr int WARP_BYTES = kRingRows * STAGE_BYTES;
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int NRC>
-__device__ __forceinline__ void store_column(uint8_t* dst, const uint32_t (&L)[NRC])
-{
-    // natural byte order k0 .. k(2*NRC-1) from registers (k_r, k_{r+NRC})
-    if constexpr (NRC == 1) {
-        __stcs(reinterpret_cast<unsigned short*>(dst), (unsigned short)__byte_perm(L[0], 0, 0x4420));
-    } else if constexpr (NRC == 2) {
-        __stcs(reinterpret_cast<uint32_t*>(dst), __byte_perm(L[0], L[1], 0x6240));
-    } else {
-        static_assert(NRC <= 4, "NRC");
-        const uint32_t a = __byte_perm(L[0], L[1], 0x6240);        // k0 k1 k4 k5
-        const uint32_t b = __byte_perm(L[NRC - 2], L[NRC - 1], 0x6240);   // k2 k3 k6 k7
-        __stcs(reinterpret_cast<uint2*>(dst), make_uint2(__byte_perm(a, b, 0x5410), __byte_perm(a, b, 0x7632)));
-    }
-}
-
-template <int NRC, int NCOL, bool DIAG, bool PAD>
-__device__ __forceinline__ void aggregate_columns_ring(const AggParams& P, const WarpWork job, int lane, uint8_t* ring)
-{
-    static_assert(NRC == 2 || NRC == 4, "NRC");
-    using R = ColumnRing<NRC, NCOL>;
-    constexpr int DPL = R::DPL, NW = R::NW, NVW = (NW + 3) / 4;
-    constexpr unsigned FULL = 0xffffffffu;
-    const Dir dir = direction(job.dir);
-    const bool fwd = dir.dy > 0;
-    const int W = P.W, H = P.H, len = H;
-    const int nact = (int)job.count;                    // paths really owned; spare columns shadow the last one
-    const bool fullGroup = nact == NCOL;
-
-    uint32_t padm[NRC];
-#pragma unroll
-    for (int r = 0; r < NRC; ++r) {
-        const int i0 = DPL * lane + r, i1 = i0 + NRC;
-        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
-    }
-    const int dbase = P.dmin + DPL * lane;              // absolute disparity of the lane's first index
-    const int dlast = P.dmin + DPL * 32 - 1;            // largest absolute disparity any lane may hold
-    const bool stores = PAD ? (DPL * lane < P.Dp) : true;
-    const uint32_t Dp = PAD ? (uint32_t)P.Dp : (uint32_t)(64 * NRC);       // bytes per pixel of a plane; a constant without padding
-    uint8_t* const planeLane = P.planes + (size_t)job.dir * P.planeStride + DPL * lane;
-    const uint32_t p1x2 = P.p1x2;
-    const uint4* const pixL = static_cast<const uint4*>(P.pixL);
-    const uint32_t* const cR4 = static_cast<const uint32_t*>(P.censusR4);
-    const uint32_t upMask = lane == 0 ? 0x00FF00FFu : 0u, dnMask = lane == 31 ? 0x00FF00FFu : 0u;   // Lp[-1] = Lp[D] = 255
-    const int half = job.dir < 4 ? 0 : 1;               // which 64-bit half of the pixel record: {P2' bytes, descriptor}
-    const uint32_t p2sel = 0x4040u | (uint32_t)((job.dir & 3) * 0x0101);   // PRMT: this direction's P2' byte into both 16-bit fields
-
-    // two trackers of column 0 (path job.firstPath): the row being fetched and the row being processed
-    struct Tracker { uint32_t pos; int tcol; };
-    const uint32_t dpos = (uint32_t)(dir.dy * W + dir.dx);
-    const int dcol = dir.dx;
-    auto advance = [&](Tracker& t) {
-        t.pos += dpos;
-        if (DIAG) {
-            t.tcol += dcol;
-            if (t.tcol >= W) { t.tcol -= W; t.pos -= (uint32_t)W; }
-            if (t.tcol < 0)  { t.tcol += W; t.pos += (uint32_t)W; }
-        }
-    };
-    auto contiguous = [&](const Tracker& t) { return fullGroup && (!DIAG || t.tcol + NCOL - 1 < W); };
-    // column c of the group at the row where column 0 is at t: same row, column (tcol + c) mod W
-    auto column_at = [&](const Tracker& t, int c, uint32_t& pc, int& tc) {
-        const int ce = c < nact ? c : nact - 1;
-        tc = t.tcol + ce; pc = t.pos + (uint32_t)ce;
-        if (tc >= W) { tc -= W; pc -= (uint32_t)W; }
-    };
-
-    // one row global -> shared: lane l copies chunk 32*j + l; chunks [0, WCH) = the descriptor span, taken from the shifted
-    // copy of the right census in which its first element is 16-byte aligned, chunks [WCH, CHUNKS) = the pixel records
-    auto issue = [&](const Tracker& t, int slot) {
-        if (contiguous(t)) {
-            const uint32_t y0 = t.pos - (uint32_t)(P.dmin + 32 * DPL - 1) + (uint32_t)P.padF;   // lane 31's first element; >= 0 by the front padding
-            const uint32_t a = (0u - y0) & 3u;
-            const uint32_t* src = cR4 + ((size_t)a * P.copyStride + y0 + a);
-            uint8_t* dst = ring + slot * R::STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < R::COPIES; ++j) {
-                const int chunk = 32 * j + lane;
-                if (chunk < R::WCH) cp_async16(dst + 16 * chunk, src + 4 * chunk);
-                else if (chunk < R::CHUNKS) cp_async16(dst + 16 * chunk, pixL + (t.pos + (uint32_t)(chunk - R::WCH)));
-            }
-        }
-        cp_async_commit();                              // a (possibly empty) group per row keeps the wait count uniform
-    };
-
-    uint32_t L[NCOL][NRC], C[NCOL][NRC], minx2[NCOL], p2w[NCOL], posc[NCOL];
-
-    // inputs of the row at t (its copies have landed): matching costs (SemiGlobalMatching.c:170-177) with registers paired
-    // (k = r, k = r + NRC), the P2' words and the pixel positions of the columns
-    auto row_inputs = [&](const Tracker& t, int slot) {
-        if (contiguous(t)) {
-            const uint8_t* st = ring + slot * R::STAGE_BYTES;
-            uint32_t v[4 * NVW], cl[NCOL];
-            const uint4* wv = reinterpret_cast<const uint4*>(st + 4 * (31 - lane) * DPL);
-#pragma unroll
-            for (int j = 0; j < NVW; ++j) {
-                const uint4 q = wv[j];
-                v[4 * j + 0] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-            }
-#pragma unroll
-            for (int c = 0; c < NCOL; ++c) {
-                const uint2 q = *reinterpret_cast<const uint2*>(st + 16 * (R::WCH + c) + 8 * half);
-                p2w[c] = q.x; cl[c] = q.y;
-                posc[c] = t.pos + c;
-            }
-            if (t.tcol < dlast) {                        // warp-uniform: some right column x - d may be negative
-#pragma unroll
-                for (int c = 0; c < NCOL; ++c) {
-                    const int nvalid = t.tcol + c - dbase + 1;
-#pragma unroll
-                    for (int r = 0; r < NRC; ++r) {
-                        const uint32_t c0 = (r < nvalid) ? (uint32_t)__popc(cl[c] ^ v[DPL - 1 + c - r]) : 127u;
-                        const uint32_t c1 = (r + NRC < nvalid) ? (uint32_t)__popc(cl[c] ^ v[DPL - 1 + c - r - NRC]) : 127u;
-                        C[c][r] = c1 * 65536u + c0;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < NCOL; ++c)
-#pragma unroll
-                    for (int r = 0; r < NRC; ++r)
-                        C[c][r] = (uint32_t)__popc(cl[c] ^ v[DPL - 1 + c - r - NRC]) * P.k65536 + (uint32_t)__popc(cl[c] ^ v[DPL - 1 + c - r]);
-            }
-            return;
-        }
-        // per-column loads, no prefetch (rare: see the header comment)
-#pragma unroll
-        for (int c = 0; c < NCOL; ++c) {
-            uint32_t pc; int tc;
-            column_at(t, c, pc, tc);
-            StepInput<NRC, uint32_t> one;
-            load_step<NRC, uint32_t>(P, pc, lane, one);
-            p2w[c] = __ldg(static_cast<const uint32_t*>(P.pixL) + 4 * (size_t)pc + 2 * half);
-            posc[c] = pc;
-            const int nvalid = tc - dbase + 1;
-#pragma unroll
-            for (int r = 0; r < NRC; ++r) {
-                const uint32_t c0 = (r < nvalid) ? (uint32_t)__popc(one.cl ^ one.v[DPL - 1 - r]) : 127u;
-                const uint32_t c1 = (r + NRC < nvalid) ? (uint32_t)__popc(one.cl ^ one.v[DPL - 1 - r - NRC]) : 127u;
-                C[c][r] = c1 * 65536u + c0;
-            }
-        }
-    };
-    auto lane_min = [&](const uint32_t (&Lc)[NRC]) {
-        uint32_t m = Lc[0];
-#pragma unroll
-        for (int r = 1; r < NRC; ++r) m = __vminu2(m, Lc[r]);
-        return __vminu2(m, __byte_perm(m, 0, 0x1032));                        // both fields = minimum of the lane
-    };
-    auto store_row = [&](bool contig) {
-        if (!stores) return;
-        if (contig) {
-            uint8_t* dst = planeLane + (size_t)posc[0] * Dp;
-#pragma unroll
-            for (int c = 0; c < NCOL; ++c) store_column<NRC>(dst + c * Dp, L[c]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCOL; ++c) store_column<NRC>(planeLane + (size_t)posc[c] * Dp, L[c]);
-        }
-    };
-
-    Tracker tf{fwd ? (uint32_t)job.firstPath : (uint32_t)((H - 1) * W + job.firstPath), job.firstPath};   // next row to fetch
-    Tracker tp = tf;                                                                                       // row being processed
-    // prologue: rows 0 .. kRingRows-1 in flight
-#pragma unroll
-    for (int k = 0; k < kRingRows; ++k) {
-        if (k < len) { issue(tf, k); advance(tf); } else cp_async_commit();
-    }
-    int slot = 0;
-    for (int s = 0; s < len; ++s) {
-        cp_async_wait<kRingRows - 1>();                 // the oldest group (row s) has landed for this lane ...
-        __syncwarp();                                   // ... and for all lanes of the warp
-        const bool contig = contiguous(tp);
-        row_inputs(tp, slot);
-        __syncwarp();                                   // every lane has read the slot: refill it with row s + kRingRows
-        if (s + kRingRows < len) { issue(tf, slot); advance(tf); } else cp_async_commit();
-        if (s == 0) {
-            // ---- first pixel of every path: L = C (SemiGlobalMatching.c:266-275)
-#pragma unroll
-            for (int c = 0; c < NCOL; ++c) {
-#pragma unroll
-                for (int r = 0; r < NRC; ++r) L[c][r] = C[c][r] | padm[r];
-                minx2[c] = __reduce_min_sync(FULL, lane_min(L[c]));
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCOL; ++c) {
-                const uint32_t p2x2 = __byte_perm(p2w[c], 0, p2sel);
-                const uint32_t negmin = __vneg2(minx2[c]);
-                const uint32_t up = __shfl_up_sync(FULL, L[c][NRC - 1], 1) | upMask;     // fields <= 255: OR with 0x00FF00FF == 255
-                const uint32_t dn = __shfl_down_sync(FULL, L[c][0], 1) | dnMask;
-                uint32_t N[NRC];
-#pragma unroll
-                for (int r = 0; r < NRC; ++r) {
-                    const uint32_t lm1 = (r == 0) ? __byte_perm(up, L[c][NRC - 1], 0x5432) : L[c][r - 1];        // Lp[d-1] of both fields
-                    const uint32_t lp1 = (r == NRC - 1) ? __byte_perm(L[c][0], dn, 0x5432) : L[c][r + 1];        // Lp[d+1]
-                    uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[c][r]);
-                    t = __viaddmin_u16x2(lp1, p1x2, t);
-                    t = __viaddmin_u16x2(t, negmin, p2x2);                         // min(. - minPrev, P2') in [0, 255]
-                    N[r] = ((C[c][r] + t) & 0x00FF00FFu) | padm[r];                // (uint8)(C + m - minPrev); fields <= 127 + 255: no carry
-                }
-#pragma unroll
-                for (int r = 0; r < NRC; ++r) L[c][r] = N[r];
-                minx2[c] = __reduce_min_sync(FULL, lane_min(L[c]));
-            }
-        }
-        store_row(contig);
-        advance(tp);
-        slot = slot + 1 == kRingRows ? 0 : slot + 1;
-    }
-    cp_async_wait<0>();
-}
-
 // ------------------------------------------------------------------------------------------------ irregular paths
 // Generic walker (path_walker.h), one path per warp; results are added to the side buffer because an
 // irregular path visits pixels that a regular path also writes.
@@ -908,24 +644,6 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
     else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD>(P, job, lane);
     else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT, PAD>(P, job, lane);
     else                          aggregate_column_like<NRV, LPPV, true, DT, PAD>(P, job, lane);
-}
-
-// Same job list, vertical / diagonal paths in the column-ring layout (32-bit descriptors, D > 64):
-// NRH/LPPH horizontal layout, NRC registers per column (D <= 64 * NRC), NCOL columns per warp, NRI irregular layout.
-template <int NRH, int LPPH, int NRC, int NCOL, int NRI, bool PAD>
-__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
-sgm_aggregate_paths_ring(const __grid_constant__ AggParams P)
-{
-    __shared__ __align__(16) uint8_t ring[kAggWarpsPerBlock][ColumnRing<NRC, NCOL>::WARP_BYTES];
-    const int widx = blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
-    const WarpWork job = P.work[widx];
-    if (widx < P.nIrregularWarps) aggregate_irregular<NRI, uint32_t, PAD>(P, job, lane);
-    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, uint32_t, PAD>(P, job, lane);
-    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, uint32_t, PAD>(P, job, lane);
-    else if (job.dir < 4)         aggregate_columns_ring<NRC, NCOL, false, PAD>(P, job, lane, ring[threadIdx.x >> 5]);
-    else                          aggregate_columns_ring<NRC, NCOL, true, PAD>(P, job, lane, ring[threadIdx.x >> 5]);
 }
 
 }  // namespace sgmb

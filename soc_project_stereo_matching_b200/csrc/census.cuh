@@ -32,11 +32,8 @@ struct CensusParams {
     uint8_t* grey[2];        // PLANAR only: converted grey images [N]
     uint32_t wR, wG, wB;     // PLANAR only: grey = (wR*R + wG*G + wB*B) >> 8
     void* left;              // DT [N]
-    void* pixL;              // per pixel of the LEFT image, 16 bytes.  32-bit descriptors: uint4 {P2' of directions 0..3 (one byte
-                             // each), descriptor, P2' of directions 4..7, descriptor}: either half is what a visit of a
-                             // direction needs besides its right-census window (see direction_penalties); 64-bit
-                             // descriptors: uint4 {lo, hi, grey, 0}
-    uint8_t p2[256];         // min(255, max(P1, P2_init / (delta + 1))) indexed by the grey difference (SemiGlobalMatching.c:335)
+    void* pixL;              // {left descriptor, grey value} per pixel of the LEFT image: uint2 (32-bit descriptors) or
+                             // uint4 {lo, hi, grey, 0} (64-bit descriptors)
     void* right4;            // DT [K][copyStride]
     size_t copyStride;       // elements per copy (padF + N + padB, multiple of 4)
     int padF;
@@ -46,36 +43,9 @@ struct CensusParams {
 constexpr int kCensusTileW = 64;
 constexpr int kCensusTileH = 8;
 
-// Adaptive penalty of every aggregation direction at pixel (x, y), one byte per direction in the order of
-// SemiGlobalMatching.c:213-220: P2' = max(P1, P2_init / (|I(p) - I(p - r)| + 1)) (:335), where p - r is the pixel a REGULAR
-// path of direction r visits before p - on the toroidal diagonals (:297-310) that is the far end of the neighbouring row when
-// p lies in the first / last column.  Clamped to 255: a penalty of 255 and any larger one select the same minimum
-// (minPrev + 255 can only win against Lp[d] <= 255 when both are 255).  Forming the penalties here, once per pixel, takes
-// the grey difference, the table lookup and the previous-grey state out of the aggregation kernel's per-visit stream.  The
-// value of a direction whose path starts at p is never used.  grey(dx, dy) reads a neighbour (tile or, at the wrap, image).
-template <typename Grey>
-__device__ __forceinline__ uint2 direction_penalties(const uint8_t (&p2)[256], int x, int y, int W, int H, Grey grey)
-{
-    const int g = grey(0, 0);
-    auto pen = [&](bool has, int gp) -> uint32_t {
-        int d = g - gp; d = d < 0 ? -d : d;
-        return has ? (uint32_t)p2[d] : 0u;
-    };
-    const bool top = y == 0, bottom = y == H - 1, first = x == 0, last = x == W - 1;
-    const uint32_t b0 = pen(!first, first ? g : grey(-1, 0));                                    // ( 1, 0): from the left
-    const uint32_t b1 = pen(!last, last ? g : grey(1, 0));                                       // (-1, 0): from the right
-    const uint32_t b2 = pen(!top, top ? g : grey(0, -1));                                        // ( 0, 1): from above
-    const uint32_t b3 = pen(!bottom, bottom ? g : grey(0, 1));                                   // ( 0,-1): from below
-    const uint32_t b4 = pen(!top, top ? g : (first ? grey(W - 1, -1) : grey(-1, -1)));           // ( 1, 1): from (y-1, x-1 mod W)
-    const uint32_t b5 = pen(!bottom, bottom ? g : (last ? grey(-(W - 1), 1) : grey(1, 1)));      // (-1,-1): from (y+1, x+1 mod W)
-    const uint32_t b6 = pen(!bottom, bottom ? g : (first ? grey(W - 1, 1) : grey(-1, 1)));       // ( 1,-1): from (y+1, x-1 mod W)
-    const uint32_t b7 = pen(!top, top ? g : (last ? grey(-(W - 1), -1) : grey(1, -1)));          // (-1, 1): from (y-1, x+1 mod W)
-    return make_uint2(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24), b4 | (b5 << 8) | (b6 << 16) | (b7 << 24));
-}
-
 template <int CW, int CH, typename DT, bool PLANAR>
 __global__ void __launch_bounds__(kCensusTileW * kCensusTileH / 2)
-sgm_census(const __grid_constant__ CensusParams P)
+sgm_census(CensusParams P)
 {
     // tile of 64 x 8 outputs, (64 + CW - 1) x (8 + CH - 1) inputs; every thread produces two horizontally adjacent outputs
     constexpr int RX = CW / 2, RY = CH / 2, K = 16 / (int)sizeof(DT);
@@ -126,23 +96,8 @@ sgm_census(const __grid_constant__ CensusParams P)
         if (which == 0) {
             static_cast<DT*>(P.left)[p] = bits;
             const uint32_t grey = tile[ty + RY][tx + o + RX];
-            if (sizeof(DT) == 4) {
-                // neighbours at distance 1 lie in the tile (halo >= 2); the wrapped ones of the toroidal diagonals are read
-                // from the image (PLANAR: converted again with the same formula)
-                auto neighbour = [&](int dx, int dy) -> int {
-                    if (dx >= -1 && dx <= 1) return tile[ty + RY + dy][tx + o + RX + dx];
-                    const size_t q = (size_t)(y + dy) * W + (x + dx);
-                    if (PLANAR) {
-                        const size_t N = (size_t)W * H;
-                        return (int)((P.wB * __ldg(img + q) + P.wG * __ldg(img + N + q) + P.wR * __ldg(img + 2 * N + q)) >> 8);
-                    }
-                    return __ldg(img + q);
-                };
-                const uint2 pen = direction_penalties(P.p2, x, y, W, H, neighbour);
-                static_cast<uint4*>(P.pixL)[p] = make_uint4(pen.x, (uint32_t)bits, pen.y, (uint32_t)bits);
-            } else {
-                static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
-            }
+            if (sizeof(DT) == 4) static_cast<uint2*>(P.pixL)[p] = make_uint2((uint32_t)bits, grey);
+            else static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
         } else {
 #pragma unroll
             for (int a = 0; a < K; ++a) static_cast<DT*>(P.right4)[a * P.copyStride + P.padF + a + p] = bits;

@@ -115,7 +115,6 @@ struct SGMB_Context {
     int lppV = 8;                 // lanes per path of the vertical / diagonal directions
     int lppH = 16;                // lanes per path of the horizontal directions
     int altLayout = 0;            // SGM_B200_DEBUG_LAYOUT: alternative kernel layouts for experiments
-    bool ilp = false;             // vertical / diagonal paths in the column-ILP layout (32-bit descriptors)
     int32_t* entryOf = nullptr;
     int nEntries = 0, nIrregular = 0;
     uint32_t p2x2[256] = {};
@@ -344,13 +343,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->altLayout = getenv("SGM_B200_DEBUG_LAYOUT") ? atoi(getenv("SGM_B200_DEBUG_LAYOUT")) : 0;   // experiments only
     if (c->altLayout == 1 && c->descBytes == 4 && c->NR == 2) c->lppV = 16;
     c->lppH = 16;
-    // 32-bit descriptors (the reference's census) with more than 64 disparities: vertical / diagonal paths in the column-ring
-    // layout (aggregate.cuh), a warp owning 8 (D <= 128) or 4 (D <= 256) adjacent paths with all 32 lanes on every one of
-    // them, and one horizontal path per warp.  SGM_B200_DEBUG_LAYOUT=3 selects the lane-group layout of round 1 for
-    // comparison, 4 keeps its horizontal layout only.
-    c->ilp = c->descBytes == 4 && c->NR >= 2 && c->altLayout != 3 && c->altLayout != 1 && c->altLayout != 2;
-    if (c->ilp) c->lppH = c->altLayout == 4 ? 16 : 32;
-    const int perWarpV = c->ilp ? agg_ring_columns(c->NR) : 32 / c->lppV;
+    const int perWarpV = 32 / c->lppV;
     const int perWarpH = 32 / c->lppH;
     std::vector<WarpWork> irregular, regular;
     std::vector<int32_t> entryOf(c->N, -1);
@@ -367,9 +360,6 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
             const size_t run = j - i;
             for (size_t k = 0; k < run; k += perWarp) {
                 size_t n = std::min<size_t>(perWarp, run - k), first = i + k;
-                // column-ILP layout: a warp whose columns are not all real paths loses its prefetched fast path, so the last
-                // group of a run is moved back to overlap its predecessor (both write identical bytes to the shared paths)
-                if (c->ilp && d >= 2 && n < (size_t)perWarp && run >= (size_t)perWarp) { first = j - perWarp; n = perWarp; }
                 regular.push_back(WarpWork{paths[first], (uint8_t)d, (uint8_t)n, 0});
             }
             i = j;
@@ -420,7 +410,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.censusL, c->N * (size_t)c->descBytes));
         CU(cudaMalloc(&s.censusR4, nCopies * c->copyStride * (size_t)c->descBytes));
         CU(cudaMemset(s.censusR4, 0, nCopies * c->copyStride * (size_t)c->descBytes));
-        CU(cudaMalloc(&s.pixL, c->N * sizeof(uint4)));
+        CU(cudaMalloc(&s.pixL, c->N * (c->descBytes == 4 ? sizeof(uint2) : sizeof(uint4))));
         CU(cudaMalloc(&s.planes, (size_t)c->nDirs * c->planeStride));
         // slots on an irregular path's toroidal diagonal are never written by K2 and must read as 0 in K3
         CU(cudaMemset(s.planes, 0, (size_t)c->nDirs * c->planeStride));
@@ -512,8 +502,6 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.grey[0] = s.img[0]; p.grey[1] = s.img[1];
         p.pixL = s.pixL;
         p.wR = (c->greyFormula == SGMB_GREY_STB) ? 77u : 76u; p.wG = 150u; p.wB = 29u;
-        for (int dg = 0; dg < 256; ++dg)      // adaptive P2 per grey difference (SemiGlobalMatching.c:335), clamped to a byte (census.cuh)
-            p.p2[dg] = (uint8_t)std::min(255, std::max((int)c->opt.p1, (int)c->opt.p2_init / (dg + 1)));
         dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
         const int threads = kCensusTileW * kCensusTileH / 2;
         if (c->descBytes == 4) {
@@ -539,7 +527,6 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
             p.wrapInterior = (maxCost + maxP2 > 255) ? 1 : 0;
         }
         memcpy(p.p2x2, c->p2x2, sizeof p.p2x2);
-        p.k65536 = 65536u;
         const int warps = c->nIrregularWarps + c->nRegularWarps;
         const int blocks = (warps + kAggWarpsPerBlock - 1) / kAggWarpsPerBlock;
         const int threads = kAggWarpsPerBlock * 32;
@@ -551,20 +538,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         if (pad) sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, true><<<blocks, threads, 0, s.stream>>>(p);  \
         else     sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, false><<<blocks, threads, 0, s.stream>>>(p); \
     } while (0)
-#define SGM_RING_LAUNCH(NRH, LPPH, NRC, NRI)                                                                                         \
-    do {                                                                                                                            \
-        if (pad) sgm_aggregate_paths_ring<NRH, LPPH, NRC, agg_ring_columns(NRC), NRI, true><<<blocks, threads, 0, s.stream>>>(p);    \
-        else     sgm_aggregate_paths_ring<NRH, LPPH, NRC, agg_ring_columns(NRC), NRI, false><<<blocks, threads, 0, s.stream>>>(p);   \
-    } while (0)
-        if (c->ilp) {
-            if (c->lppH == 32) {
-                if (c->NR == 2) SGM_RING_LAUNCH(2, 32, 2, 2);
-                else            SGM_RING_LAUNCH(4, 32, 4, 4);
-            } else {
-                if (c->NR == 2) SGM_RING_LAUNCH(4, 16, 2, 2);
-                else            SGM_RING_LAUNCH(8, 16, 4, 4);
-            }
-        } else if (c->descBytes == 4) {
+        if (c->descBytes == 4) {
             if (c->NR == 1)                           SGM_AGG_LAUNCH(2, 16, 4, 8, 1, uint32_t);
             else if (c->NR == 2 && c->altLayout == 1) SGM_AGG_LAUNCH(4, 16, 4, 16, 2, uint32_t);
             else if (c->NR == 2)                      SGM_AGG_LAUNCH(4, 16, 8, 8, 2, uint32_t);
@@ -575,7 +549,6 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
             else                 SGM_AGG_LAUNCH(8, 16, 8, 16, 4, desc64_t);
         }
 #undef SGM_AGG_LAUNCH
-#undef SGM_RING_LAUNCH
         if (timeAgg) CU(cudaEventRecordWithFlags(s.evAgg1, s.stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ++nk;
         if (int rc = mark("sgm_aggregate_paths")) return rc;
