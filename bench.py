@@ -11,11 +11,19 @@ census (the "9x7" of the config text has no reference implementation, SURVEY.md 
 
 One step = one stereo pair per GPU.  Metric = million disparity evaluations per second,
 MDE/s = W*H*D*frames/s / 1e6, whole job (all ranks).
-  value  device-resident: K frames enqueued back to back, timed with CUDA events on the launching stream.
-  e2e    the reference-facing call SGM_Match() with pinned HOST buffers: H2D of both images, all kernels
+  value  device-resident: a CUDA graph of K frames, timed with CUDA events on the launching stream and replayed
+         `--replays` times; `value` comes from the median replay (max over ranks), p95 / min beside it.
+  e2e    the reference-facing call SGM_Match() with page-locked HOST buffers: H2D of both images, all kernels
          (hot path + the reference's speckle filter and in-place median, which SGM_Match always runs), D2H
-         of the disparity map, every step.
-  roofline      dominant kernel (K2 aggregation): algorithmic bytes of the SURVEY 8d model / its measured duration.
+         of the disparity map, every step.  `e2e_pageable`: the same call with malloc'd (pageable) buffers,
+         which is what the reference demo passes (main.c:25-26,81).
+  kernels       every kernel of one SGM_Match frame, CUDA events around each launch, with the bytes it has to move.
+  roofline      dominant kernel (K2 aggregation).  `frac` is the SURVEY 8d model (algorithmic bytes of the reference's
+                read-modify-write formulation / measured duration / measured HBM peak); the kernel moves 4x fewer bytes
+                and is NOT HBM-bound: `bound` names what binds it per ncu, `frac_measured_traffic` is its real share of
+                the HBM peak and `issue_frac` its share of the instruction-issue peak.  ncu-derived fields are read
+                from profiles/traffic.json (a committed capture: "static": true), not measured in this run.
+  pool_c4       config C4 through the library's own multi-GPU sharding (SGMB_Pool over all visible GPUs).
   cpu_baseline  the reference's own C code on this box's host cores (oracle/cpu_bench.py), N=1 only.
 """
 from __future__ import annotations
@@ -118,6 +126,44 @@ def bench_reference(args, rank: int, world: int) -> int:
     return 0
 
 
+def bench_pool_c4(sgm, torch, n_pairs: int, slots: int, de_per_frame: int) -> dict:
+    """C4: n_pairs KITTI-shaped pairs, D=128, 4 paths, host buffers -> SGMB_PoolMatchBatch on 1 GPU and on all visible
+    GPUs, hot-path pipeline and SGM_Match's full pipeline.  Eight distinct seeded pairs are cycled through the batch."""
+    from soc_project_stereo_matching_b200.synth import make_pair
+    ndev_all = sgm.lib.SGMB_DeviceCount()
+    opt4 = sgm.default_option(max_disparity=D, num_paths=4, is_remove_speckles=True)
+    base = [make_pair(W, H, D, seed=0xB200 + k, texture="scene" if k % 3 == 0 else "noise")[:2] for k in range(8)]
+    h_l = torch.empty((n_pairs, H, W), dtype=torch.uint8).pin_memory()
+    h_r = torch.empty((n_pairs, H, W), dtype=torch.uint8).pin_memory()
+    h_o = torch.empty((n_pairs, H, W), dtype=torch.float32).pin_memory()
+    for k in range(n_pairs):
+        h_l[k] = torch.from_numpy(base[k % 8][0]); h_r[k] = torch.from_numpy(base[k % 8][1])
+    import ctypes as C
+    pa = lambda t: (C.c_void_p * n_pairs)(*[t[k].data_ptr() for k in range(n_pairs)])
+    pl, pr, po = pa(h_l), pa(h_r), pa(h_o)
+    out = {"workload": f"C4: {n_pairs} KITTI-shaped pairs 1242x375, D=128, 4 paths, page-locked host buffers in and out",
+           "api": "SGMB_PoolMatchBatch (contiguous shards, one host thread + context per device)", "slots_per_device": slots,
+           "h2d_bytes_per_pair": 2 * W * H, "d2h_bytes_per_pair": 4 * W * H, "gpus_visible": ndev_all}
+    for tag, flags in (("hotpath", sgm.PIPE_HOTPATH), ("sgm_match", sgm.PIPE_REFERENCE)):
+        res = {}
+        for ndev in sorted({1, ndev_all}):
+            with sgm.Pool(list(range(ndev)), slots_per_device=slots) as pool:
+                pool.configure(W, H, opt4, flags)
+                sgm._check(sgm.lib.SGMB_PoolMatchBatch(pool._h, pl, pr, po, min(n_pairs, 4 * slots * ndev)))     # warm-up: graphs, staging
+                best = None
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    sgm._check(sgm.lib.SGMB_PoolMatchBatch(pool._h, pl, pr, po, n_pairs))
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+            res[ndev] = {"n_gpus": ndev, "ms_per_batch": best * 1e3, "frames_per_s": n_pairs / best,
+                         "value": n_pairs * de_per_frame / best / 1e6, "unit": "MDE/s"}
+        for ndev, r in res.items():
+            r["efficiency_vs_n1"] = r["frames_per_s"] / (ndev * res[1]["frames_per_s"])
+        out[tag] = list(res.values())
+    return out
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -126,6 +172,8 @@ def main() -> int:
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--inflight", type=int, default=4, help="frames in flight for the extra batched-throughput figure")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replays", type=int, default=25, help="replays of the K-frame graph behind `value` (median reported)")
+    ap.add_argument("--pool-pairs", type=int, default=256, help="pairs of the C4 batch run through SGMB_Pool (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -179,7 +227,9 @@ def main() -> int:
         cpu = {"value": r["mde_per_s"], "unit": "MDE/s", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{r['frames_per_step']} frames per step (one process per core), 2 steps, census..LR check only "
                          f"(same span as `value`), {'compiled reference SemiGlobalMatching.c' if r['kind'] == 'reference' else 'oracle port'}",
-               "single_frame_seconds": r["single_frame_seconds"], "frames_per_s": r["frames_per_s"]}
+               "single_frame_seconds": r["single_frame_seconds"], "frames_per_s": r["frames_per_s"],
+               "single_core": {"value": W * H * D / r["single_frame_seconds"] / 1e6, "unit": "MDE/s", "cores": 1,
+                               "note": "fastest single frame of one worker process while all cores were busy (latency of the reference)"}}
 
     # ---- inputs: one seeded pair per rank, resident on the device and in pinned host memory
     left, right, _ = make_pair(W, H, D, seed=0xB200 + rank, texture="noise")
@@ -200,11 +250,17 @@ def main() -> int:
     ctx.run_device(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), args.warmup, False)
     barrier()
     t0 = time.perf_counter()
-    total_ms, agg_ms = ctx.run_device(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), args.steps, True)
+    replay_ms, agg_ms = ctx.run_device_replays(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), args.steps, max(1, args.replays))
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    total_ms = max_over_ranks(total_ms)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / max(1, args.replays)
+    total_ms = max_over_ranks(float(np.median(replay_ms)))          # K steps: the median replay, the slowest rank
+    p95_ms = max_over_ranks(float(np.percentile(replay_ms, 95)))
+    min_ms = max_over_ranks(float(np.min(replay_ms)))
     value = world * args.steps * de_per_frame / (total_ms * 1e-3) / 1e6
+    # every kernel of one SGM_Match frame (hot path + speckle filter + median), CUDA events around each launch
+    ctx.set_pipeline(sgm.PIPE_REFERENCE)
+    kernel_times = ctx.time_kernels(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), 3, 20)
+    ctx.set_pipeline(sgm.PIPE_HOTPATH)
     gpu_launches = world * args.steps * launches_per_frame          # all ranks
     # per-frame latency with a host sync after every frame (what a latency-bound caller sees), L2 flushed in between
     lat_ms, _ = ctx.time_device(d_left.data_ptr(), d_right.data_ptr(), d_out.data_ptr(), 3, min(args.steps, 50), True)
@@ -224,6 +280,17 @@ def main() -> int:
     assert ok, sgm.last_error()
     e2e_value = world * args.steps * de_per_frame / e2e_s / 1e6
     gctx_launches = 3 + 3 + 2
+    # the same call with pageable (malloc'd) buffers: what the reference demo passes (main.c:25-26,81)
+    pg_l, pg_r, pg_o = left.copy(), right.copy(), np.zeros((H, W), np.float32)
+    for _ in range(args.warmup):
+        assert sgm.SGM_Match(pg_l, pg_r, pg_o)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sgm.SGM_Match(pg_l, pg_r, pg_o)
+    barrier()
+    e2e_pg_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.array_equal(pg_o.view(np.uint32), np_o.view(np.uint32)), "pageable and page-locked calls disagree"
     # same call sequence restricted to the hot path (no speckle filter / median), host buffers
     ctx.set_pipeline(sgm.PIPE_HOTPATH)
     for _ in range(args.warmup):
@@ -305,6 +372,15 @@ def main() -> int:
         census97 = {"census": "9x7, 64-bit descriptors, popcll(xor) cost (extension; parity pinned by the oracle's generalisation only)",
                     "value": world * args.steps * de_per_frame / (c_ms * 1e-3) / 1e6, "unit": "MDE/s",
                     "ms_per_step": c_ms / args.steps, "aggregation_kernel_ms": float(np.mean(c_agg))}
+    # ---- config C4 as BASELINE.json states it, through the library's own multi-GPU sharding: 256 pairs (4 paths) in
+    #      page-locked host buffers, SGMB_Pool over 1 and over all visible GPUs (contiguous shards, one host thread and
+    #      one context per device, no inter-GPU communication); rank 0 only, after the per-rank sections
+    pool_c4 = None
+    if args.pool_pairs > 0:
+        barrier()
+        if rank == 0:
+            pool_c4 = bench_pool_c4(sgm, torch, args.pool_pairs, args.inflight, de_per_frame)
+        barrier()
     clocks = sampler.stop()
 
     if rank == 0:
@@ -321,12 +397,24 @@ def main() -> int:
         agg_alg_bytes = (4 * PATHS - 2) * de_per_frame
         frame_alg_bytes = ctx.model_bytes_per_frame()
         achieved = agg_alg_bytes / (agg_avg_ms * 1e-3) / 1e9
-        traffic, ncu_facts = None, None
+        # ncu facts of the committed capture (NOT measured in this run: "static": true)
+        ncu_facts = {}
         try:
             ncu_facts = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = ncu_facts.get("aggregate_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
+        traffic = ncu_facts.get("aggregate_dram_bytes_per_launch")
+        sm_hz = (clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))) * 1e6
+        issue_frac = None
+        if ncu_facts.get("warp_instructions"):
+            issue_frac = ncu_facts["warp_instructions"] / (148 * 4 * sm_hz * agg_avg_ms * 1e-3)
+        # bytes every kernel of the frame has to move in this implementation (planes written once by K2, read once by K3)
+        n_px, dp = W * H, (D + 15) // 16 * 16
+        plan_bytes = {"sgm_census": n_px * (2 + 4 + 8 + 16), "sgm_aggregate_paths": n_px * (PATHS * dp + 12 + 16),
+                      "sgm_reduce_wta_lr": n_px * (PATHS * dp + 2 * 16 * 2 + 8), "speckle_init": n_px * 12, "speckle_merge": n_px * 8,
+                      "speckle_count": n_px * 8, "median_prepare": n_px * (4 + 8 + 20), "median_wavefront": n_px * (20 + 4)}
+        kernels = [{"name": k, "ms": ms, "plan_bytes": plan_bytes.get(k), "frac_hbm": (plan_bytes[k] / (ms * 1e-3) / 1e9 / peak) if k in plan_bytes and ms > 0 else None}
+                   for k, ms in kernel_times]
         line = {
             "metric": METRIC, "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -335,26 +423,37 @@ def main() -> int:
                        "l2": "inputs larger than L2: per-step working set 954 MB (8 uint8 path planes written + read once) > 126 MB L2, no flush needed",
                        "parallelism": f"{world} independent replicas, one frame per GPU per step, no collective"},
             "frames_per_s": world * args.steps / (total_ms * 1e-3),
-            "wall_ms_per_step": wall_ms / args.steps,
+            "timing": {"replays": int(max(1, args.replays)), "statistic": "median over replays of one CUDA graph of K frames (max over ranks)",
+                       "ms_per_step_p95": p95_ms / args.steps, "ms_per_step_min": min_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},
             "latency_ms": {"median": float(np.median(lat_ms)), "p95": float(np.percentile(lat_ms, 95)), "note": "single frame, host sync + L2 flush between frames"},
-            "roofline": {"bound": "hbm", "kernel": "sgm_aggregate_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "issue", "bound_note": "dependent-instruction latency / issue rate of the integer DP (ALU pipe), not HBM: see frac_measured_traffic",
+                         "kernel": "sgm_aggregate_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_note": "SURVEY 8d model: algorithmic bytes of the reference's formulation (S read-modify-written per direction)",
+                         "traffic": traffic, "frac_measured_traffic": (traffic / (agg_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "issue_frac": issue_frac, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": agg_alg_bytes, "kernel_ms": agg_avg_ms,
                          "kernel_share_of_step": agg_avg_ms / (total_ms / args.steps),
                          "dtype_note": "u8 path costs / u16 sums as packed u16x2 DPX integer ops; f32 only in sub-pixel, LR check, median",
-                         "ncu": ncu_facts,
+                         "ncu": dict(ncu_facts, static=True, note="committed ncu capture, not measured in this run"),
                          "frame": {"algorithmic_bytes": frame_alg_bytes, "achieved": frame_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9,
                                    "frac": frame_alg_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
-                                   "plan_bytes": ctx.plan_bytes_per_frame()}},
+                                   "plan_bytes": ctx.plan_bytes_per_frame(),
+                                   "frac_plan_bytes": ctx.plan_bytes_per_frame() / (total_ms / args.steps * 1e-3) / 1e9 / peak}},
+            "kernels": kernels,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "MDE/s", "h2d_bytes_per_step": 2 * W * H, "d2h_bytes_per_step": 4 * W * H,
                     "ms_per_step": e2e_s / args.steps * 1e3, "span": "SGM_Match: hot path + speckle filter + in-place median",
+                    "host_buffers": "page-locked",
                     "hotpath_only": {"value": world * args.steps * de_per_frame / e2e_hot_s / 1e6, "ms_per_step": e2e_hot_s / args.steps * 1e3}},
+            "e2e_pageable": {"value": world * args.steps * de_per_frame / e2e_pg_s / 1e6, "unit": "MDE/s", "ms_per_step": e2e_pg_s / args.steps * 1e3,
+                             "host_buffers": "pageable (malloc'd numpy arrays, as main.c:25-26,81 passes)", "h2d_bytes_per_step": 2 * W * H,
+                             "d2h_bytes_per_step": 4 * W * H},
             "gpu_launches": gpu_launches,
-            "gpu_launches_note": f"{launches_per_frame} kernels per hot-path frame in the `value` region; SGM_Match launches {gctx_launches} per frame",
+            "gpu_launches_note": f"{launches_per_frame} kernels per hot-path frame in the `value` region (x {max(1, args.replays)} replays in total); SGM_Match launches {gctx_launches} per frame",
             "batched": batched,
             "e2e_batched": e2e_batched,
             "batched_c4": batched_c4,
+            "pool_c4": pool_c4,
             "census9x7": census97,
             "clocks": clocks,
         }

@@ -51,7 +51,8 @@ enum {
     SGMB_STAGE_DISP_LR       = 5,  /* float  [N]     after LR check             SemiGlobalMatching.c:445-470 */
     SGMB_STAGE_DISP_SPECKLE  = 6,  /* float  [N]     after speckle removal      SemiGlobalMatching.c:585-642 (needs SGMB_PIPE_TAPS) */
     SGMB_STAGE_DISP_FINAL    = 7,  /* float  [N]     what SGM_Match returns                                   */
-    SGMB_STAGE_SPECKLE_LABELS = 8, /* int32  [2*N]   speckle filter scratch: component root per pixel (-1: invalid), then size per root */
+    SGMB_STAGE_SPECKLE_LABELS = 8, /* int32  [2*N]   speckle filter scratch: component root per pixel (-1: invalid), then size per root
+                                      (exact below min_speckle_area, "at least min_speckle_area" above: counting stops there) */
     SGMB_STAGE_GREY_LEFT     = 9,  /* uint8  [N]     grey images the path ran on (after SGMB_MatchFrame: the fused conversion's output) */
     SGMB_STAGE_GREY_RIGHT    = 10,
     SGMB_STAGE_PATH_PLANE_0  = 16  /* uint8  [N*D]   +r: L_r(p,d) of direction r (order of SemiGlobalMatching.c:213-220) as written by

@@ -75,7 +75,7 @@ for _ in range(200):
     t0 = time.perf_counter(); call(); ts.append(time.perf_counter() - t0)
 print(np.median(ts) * 1e3, np.percentile(ts, 95) * 1e3)
 ''' % ROOT
-    for kind, env in (("pinned", {}), ("pageable_staged", {}), ("pageable_direct", {"SGM_B200_PAGEABLE": "direct"})):
+    for kind, env in (("pinned", {}), ("pageable", {})):
         e = dict(os.environ); e.update(env)
         out = subprocess.run([sys.executable, "-c", code, kind], capture_output=True, text=True, env=e)
         try:

@@ -71,11 +71,14 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b)
     }
 }
 
-// grid (ceil(W/32), H), block 32: one warp per 32-pixel row segment.
-__global__ void __launch_bounds__(32) speckle_init(const float* __restrict__ disp, int* __restrict__ lab, int* __restrict__ size,
-                                                   int W, int H, float diff)
+// grid (ceil(W/32), ceil(H/8)), block (32, 8): one warp per 32-pixel row segment, eight rows per CTA (one-warp CTAs -
+// 14625 of them at C2 - were bound by the CTA launch rate: 14 us for a kernel that moves 4 MB).
+constexpr int kSpeckleRowsPerBlock = 8;
+__global__ void __launch_bounds__(32 * kSpeckleRowsPerBlock) speckle_init(const float* __restrict__ disp, int* __restrict__ lab,
+                                                                        int* __restrict__ size, int W, int H, float diff)
 {
-    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y;
+    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y * kSpeckleRowsPerBlock + threadIdx.y;
+    if (y >= H) return;                                              // whole warps leave together
     const bool in = x < W;
     const int p = y * W + x;
     const float d = in ? disp[p] : __int_as_float(0x7f800000);
@@ -111,17 +114,21 @@ __global__ void speckle_merge(const float* __restrict__ disp, int* lab, int W, i
     if (pp_edge(c, br, diff) && !(eR && pp_edge(r, br, diff)) && !(pp_edge(c, b, diff) && pp_edge(b, br, diff))) uf_union(lab, p, q + 1);
 }
 
-// grid (ceil(W/32), H), block 32: flatten and add each warp segment's length to its root.
-__global__ void __launch_bounds__(32) speckle_count(int* lab, int* size, int W, int H)
+// grid (ceil(W/32), ceil(H/8)), block (32, 8): flatten and add each warp segment's length to its root.  Only the
+// comparison size < minArea is ever made (SemiGlobalMatching.c:633), so a root whose count has already reached minArea
+// receives no further additions: a good disparity map is one huge component, and ~15 000 atomics on its single counter
+// were most of this kernel's time.  size[root] is therefore exact below minArea and "at least minArea" above.
+__global__ void __launch_bounds__(32 * kSpeckleRowsPerBlock) speckle_count(int* lab, int* size, int W, int H, int minArea)
 {
-    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y;
+    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y * kSpeckleRowsPerBlock + threadIdx.y;
+    if (y >= H) return;
     const bool in = x < W;
     const int p = y * W + x;
     int root = -1;
     if (in && lab[p] >= 0) { root = uf_root(lab, p); lab[p] = root; }
     // lanes with the same root inside the warp add once
     const unsigned peers = __match_any_sync(0xffffffffu, root);
-    if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));
+    if (root >= 0 && lane == __ffs(peers) - 1 && __ldcg(&size[root]) < minArea) atomicAdd(&size[root], __popc(peers));
 }
 
 // Returns the number of kernels launched.  The component sizes are applied by the consumer (K5a below, or
@@ -130,18 +137,17 @@ constexpr int kSpeckleLabelLaunches = 3;
 
 // `mark(name)` is called after every launch (per-kernel timing hook of the host layer; a no-op otherwise).
 template <typename Mark>
-static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, int W, int H, float diff, cudaStream_t st, Mark mark)
+static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, int W, int H, float diff, int minArea, cudaStream_t st, Mark mark)
 {
     const int n = W * H;
     int* lab = scratch;
     int* size = scratch + n;
-    dim3 gseg((W + 31) / 32, H);
-    speckle_init<<<gseg, 32, 0, st>>>(in, lab, size, W, H, diff);
+    dim3 b(32, kSpeckleRowsPerBlock), g((W + 31) / 32, (H + kSpeckleRowsPerBlock - 1) / kSpeckleRowsPerBlock);
+    speckle_init<<<g, b, 0, st>>>(in, lab, size, W, H, diff);
     mark("speckle_init");
-    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     speckle_merge<<<g, b, 0, st>>>(in, lab, W, H, diff);
     mark("speckle_merge");
-    speckle_count<<<gseg, 32, 0, st>>>(lab, size, W, H);
+    speckle_count<<<g, b, 0, st>>>(lab, size, W, H, minArea);
     mark("speckle_count");
     return kSpeckleLabelLaunches;
 }
@@ -295,9 +301,57 @@ __device__ __forceinline__ void median_fold(const float* A, int lane4, float a, 
     e5 = fminf(fminf(A5, fmaxf(A4, B1)), fminf(fmaxf(A3, B2), fmaxf(A2, B3)));
 }
 
-// 32 steps (one exchange batch, kMedianBatch bulk-copy blocks); ringLane: the lane's view of the first of them.  PRED: some lane's column may fall outside the row.
+// Values of the last row of the group above (row 32g - 1), eight columns at a time.  The producer publishes every column as
+// it is computed; the consumer takes them in pieces of kMedianFeed columns - lanes 0 .. kMedianFeed-1 hold the current
+// piece, the next piece is requested when the current one is taken over and verified (tag) when its turn comes.  The
+// piece size sets how far a group must trail its predecessor: 62 steps by construction (lane 31 of the group above is 62
+// steps behind its lane 0) + one piece + one piece of prefetch distance + the store-to-poll latency.  With 32-column
+// pieces fetched 32 steps ahead (round 1) a group trailed by ~170 steps = 7.6 us, and the whole filter was groups x that.
+constexpr int kMedianFeed = 8;
+struct AboveFeed {
+    const unsigned long long* aboveX;
+    int W, lane;
+    unsigned tagBase;
+    unsigned long long next;     // requested word of the next piece (lanes < kMedianFeed)
+    float cur;                   // lanes < kMedianFeed: out(32g - 1, first column of the piece + lane)
+#ifdef SGM_MEDIAN_DEBUG
+    long long polls = 0, pieces = 0, waited = 0; unsigned long long tFirst = 0;
+#endif
+
+    __device__ __forceinline__ unsigned long long request(int col) const
+    {
+        return (lane < kMedianFeed && col >= 0 && col < W) ? ld_relaxed_gpu_u64(aboveX + col) : 0ull;
+    }
+    // make the piece starting at column col0 current (wait until the producer has published all of it), request the next one
+    __device__ __forceinline__ void advance(int col0)
+    {
+        const int col = col0 + lane;
+        const bool need = lane < kMedianFeed && col >= 0 && col < W;
+        unsigned long long v = next;
+        unsigned spins = 0;
+#ifdef SGM_MEDIAN_DEBUG
+        const long long w0 = clock64(); ++pieces;
+#endif
+        while (!__all_sync(0xffffffffu, !need || (unsigned)(v >> 32) == (tagBase | (unsigned)(col + 1)))) {
+            __nanosleep(64);                             // do not hammer the L2 line the producer is storing to
+            if (++spins > (1u << 24)) __trap();          // ~2 s without progress: fail the launch instead of hanging the device
+            v = request(col);
+#ifdef SGM_MEDIAN_DEBUG
+            ++polls;
+#endif
+        }
+#ifdef SGM_MEDIAN_DEBUG
+        if (col0 >= 8) waited += clock64() - w0;
+        if (col0 >= 0 && !tFirst) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tFirst));
+#endif
+        cur = __uint_as_float((unsigned)v);
+        next = request(col + kMedianFeed);
+    }
+};
+
+// 32 steps (kMedianBatch bulk-copy blocks); ringLane: the lane's view of the first of them.  PRED: some lane's column may fall outside the row.
 template <bool HAS_ABOVE, bool PRED, typename Wait, typename Refill>
-__device__ __forceinline__ void median_superblock(MedianLane& st, const float* ringLane, float batch, float* op, unsigned long long* xp,
+__device__ __forceinline__ void median_superblock(MedianLane& st, const float* ringLane, AboveFeed& feed, int colAbove0, float* op, unsigned long long* xp,
                                                   int jBase, int Wrow, bool publishes, unsigned tag0, int lane, Wait wait, Refill refill)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -308,6 +362,7 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
 #pragma unroll
         for (int e = 0; e < BS; ++e) {
             const int off = k * BS + e;
+            if (HAS_ABOVE && off % kMedianFeed == 0) feed.advance(colAbove0 + off);
             float e4, e5;
             median_fold(ringLane + (k * BS + e) * 5 * 32, 4 * lane, st.a, st.b, st.left, e4, e5);
             const float o = fminf(fmaxf(st.c, e4), e5);
@@ -318,7 +373,7 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
             st.left = o;
             float up = __shfl_up_sync(FULL, o, 1);       // out(i-1, j+2): the c of the next step
             if (HAS_ABOVE) {
-                const float fromAbove = __shfl_sync(FULL, batch, off);
+                const float fromAbove = __shfl_sync(FULL, feed.cur, off % kMedianFeed);
                 if (lane == 0) up = fromAbove;
             }
             st.a = st.b; st.b = st.c; st.c = up;
@@ -369,43 +424,18 @@ __device__ __forceinline__ void median_wavefront_body(const int g, const float* 
     __syncwarp();
 
 #ifdef SGM_MEDIAN_DEBUG
-    unsigned long long tStart, tFirst = 0, tEnd; long long pollCount = 0, waitCycles = 0;
+    unsigned long long tStart, tEnd;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tStart));
 #endif
     MedianLane st{0.f, 0.f, 0.f, 0.f};
-    // exchange with the group above: lane k of `batch` holds out(32g-1, base + k) for the 32 steps of a super-block;
-    // `ahead` is the next batch, fetched one super-block early and verified when it becomes current
-    unsigned long long ahead = 0;
+    // exchange with the group above (AboveFeed): step s needs out(32g - 1, s + 2) for its successor
+    AboveFeed feed{aboveX, W, lane, tagBase, 0ull, 0.f};
+    if (HAS_ABOVE) feed.next = feed.request(2 - kMedianFrontPad + lane);
     const int nSuper = nBlocks / NB;
     for (int sb = 0; sb < nSuper; ++sb) {
         const int slot0 = (sb * NB) % NR;                // ring slots of this super-block: slot0 .. slot0 + NB - 1
         const float* ringLane = &ring[slot0][0][0][0];
         const int s0 = sb * NB * BS - kMedianFrontPad;   // first step of the super-block
-        float batch = 0.f;
-        if (HAS_ABOVE) {
-            const int col = s0 + 2 + lane;               // step s needs out(32g-1, s + 2) for its successor
-            const bool inRow = col >= 0 && col < W;
-            unsigned long long v = (sb > 0) ? ahead : (inRow ? ld_relaxed_gpu_u64(aboveX + col) : 0ull);
-#ifdef SGM_MEDIAN_DEBUG
-            long long w0 = clock64();
-#endif
-            unsigned spins = 0;
-            while (!__all_sync(FULL, !inRow || (unsigned)(v >> 32) == (tagBase | (unsigned)(col + 1)))) {
-                __nanosleep(200);                        // do not hammer the L2 line the producer is storing to
-                if (++spins > (1u << 23)) __trap();      // ~2 s without progress: fail the launch instead of hanging the device
-                v = inRow ? ld_relaxed_gpu_u64(aboveX + col) : 0ull;
-#ifdef SGM_MEDIAN_DEBUG
-                ++pollCount;
-#endif
-            }
-#ifdef SGM_MEDIAN_DEBUG
-            if (sb >= 4) waitCycles += clock64() - w0;
-            if (sb == 3) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tFirst));
-#endif
-            batch = __uint_as_float((unsigned)v);
-            const int colNext = col + NB * BS;
-            ahead = (colNext >= 0 && colNext < W) ? ld_relaxed_gpu_u64(aboveX + colNext) : 0ull;
-        }
         const int jBase = s0 - 2 * lane;
         float* op = outRow + jBase;
         unsigned long long* xp = myX + jBase;
@@ -429,12 +459,13 @@ __device__ __forceinline__ void median_wavefront_body(const int g, const float* 
         };
         // all 32 lanes are inside their rows for every step of the super-block <=> s0 >= 62 and s0 + 31 < W (and the row exists)
         const bool interior = s0 >= 62 && s0 + NB * BS <= W;
-        if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
-        else          median_superblock<HAS_ABOVE, true>(st, ringLane, batch, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, feed, s0 + 2, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        else          median_superblock<HAS_ABOVE, true>(st, ringLane, feed, s0 + 2, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
     }
 #ifdef SGM_MEDIAN_DEBUG
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
-    if (lane == 0) printf("median g=%d start=%llu first4=%llu end=%llu dur_us=%.1f polls=%lld waitcyc_after4=%lld nSuper=%d\n", g, tStart % 100000000ull, tFirst % 100000000ull, tEnd % 100000000ull, (tEnd - tStart) * 1e-3, pollCount, waitCycles, nSuper);
+    if (lane == 0) printf("median g=%d start=%llu first=%llu end=%llu dur_us=%.1f pieces=%lld polls=%lld waited_cyc_after_first=%lld\n", g, tStart % 100000000ull,
+                          feed.tFirst % 100000000ull, tEnd % 100000000ull, (tEnd - tStart) * 1e-3, feed.pieces, feed.polls, feed.waited);
 #endif
 }
 

@@ -120,7 +120,7 @@ struct SGMB_Context {
     uint32_t p2x2[256] = {};
     uint32_t p1x2 = 0;
     // K3 launch shape: lanes per pixel (power of two >= Dp / 16), columns per tile, dynamic shared memory
-    int wtaCPP = 8, wtaTW = 32;
+    int wtaCPP = 8, wtaTW = 32, wtaRingRows = 0;
     size_t wtaSmem = 0;
     // L2 flush scratch for SGMB_TimeDevice
     uint8_t* flushBuf = nullptr;
@@ -281,11 +281,12 @@ static int wta_prepare(SGMB_Context* c)
 {
     c->wtaCPP = CPP;
     c->wtaTW = WtaShape<CPP>::kTW;
-    c->wtaSmem = (size_t)(2 * c->wtaTW + c->D) * WtaShape<CPP>::kRS * sizeof(uint16_t);
+    c->wtaSmem = WtaShape<CPP>::ring_bytes(c->D);
+    c->wtaRingRows = WtaShape<CPP>::ring_rows(c->D);
     // The attribute belongs to the function on this device, i.e. to every context of the process: it is set to the largest
     // ring of the CPP class (D = 16 * CPP), never to this context's own size - a later context with a smaller D must not
     // lower the limit under a live context with a larger one.
-    const int classMax = (2 * WtaShape<CPP>::kTW + 16 * CPP) * WtaShape<CPP>::kRS * (int)sizeof(uint16_t);
+    const int classMax = (int)WtaShape<CPP>::ring_bytes(16 * CPP);
     CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
     CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
     CU(cudaFuncSetAttribute(sgm_reduce_wta_lr<CPP, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, classMax));
@@ -563,7 +564,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.W = W; p.H = H; p.D = D; p.Dp = c->Dp; p.dmin = c->opt.min_disparity;
         p.checkUnique = c->opt.is_check_unique; p.oneMinusRatio = 1 - c->opt.uniqueness_ratio;
         p.checkLR = c->opt.is_check_lr; p.lrThres = c->opt.lrcheck_thres;
-        p.ringCols = 2 * c->wtaTW + D;
+        p.ringCols = c->wtaRingRows;
         p.rightRow = s.rightRow;
         p.records = s.wtaRecords;
 #define SGM_WTA_LAUNCH(CPP)                                                                                          \
@@ -588,7 +589,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     float* cur = lrOut;
     const int32_t* lab = nullptr;
     if (doSpeckle) {
-        nk += launch_speckle_labels(cur, s.labels, W, H, 1.0f, s.stream, mark);
+        nk += launch_speckle_labels(cur, s.labels, W, H, 1.0f, c->opt.min_speckle_area, s.stream, mark);
         lab = s.labels;
         if (!doMedian) {
             speckle_apply<<<((int)c->N + 255) / 256, 256, 0, s.stream>>>(cur, s.dispSpeckle, lab, lab + c->N, (int)c->N, c->opt.min_speckle_area);
@@ -642,10 +643,14 @@ static float* frame_result(SGMB_Context* c, Slot& s)
 
 // ------------------------------------------------------------------------------------------------ host <-> device copies
 // Page-locked caller memory (cudaHostAlloc / cudaHostRegister / SGMB_HostAlloc) is read and written by the copy engine
-// directly.  Pageable memory (malloc, static arrays: what the reference demo passes, main.c:25-26,81) makes
-// cudaMemcpyAsync stage synchronously inside the driver; here it goes through the slot's own page-locked staging buffers
-// instead: one memcpy + ONE asynchronous copy for both images, and the result is copied out of the staging buffer once the
-// stream has drained.  SGM_B200_PAGEABLE=direct hands pageable pointers to cudaMemcpyAsync as they are (measurement aid).
+// directly and cudaMemcpyAsync is truly asynchronous.  Pageable memory (malloc, static arrays: what the reference demo
+// passes, main.c:25-26,81) makes cudaMemcpyAsync stage through the driver's own buffers and block the calling thread.
+//   * A single frame (SGM_Match / SGMB_Match) hands pageable pointers to the driver as they are: measured at C2 that
+//     is as fast as staging through buffers of our own (0.82 ms per call either way, profiles/r2_o_kernels.jsonl;
+//     page-locked buffers: 0.68 ms).
+//   * A batch would lose its pipelining to those blocking copies, so there pageable buffers are staged through
+//     page-locked buffers owned by the slot: one memcpy + ONE asynchronous copy for both images, and the result is
+//     copied out of the staging buffer when the slot is reused or the batch ends.
 static bool host_is_pinned(const void* p)
 {
     cudaPointerAttributes a{};
@@ -653,11 +658,6 @@ static bool host_is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-static bool pageable_direct()
-{
-    static const bool v = [] { const char* e = getenv("SGM_B200_PAGEABLE"); return e && !strcmp(e, "direct"); }();
-    return v;
-}
 
 // Result of the slot's previous frame still sitting in the staging buffer -> the caller's pageable buffer.
 static int flush_pending_out(SGMB_Context* c, Slot& s)
@@ -669,10 +669,10 @@ static int flush_pending_out(SGMB_Context* c, Slot& s)
     return SGMB_OK;
 }
 
-static int copy_in(SGMB_Context* c, Slot& s, const uint8_t* L, const uint8_t* R)
+static int copy_in(SGMB_Context* c, Slot& s, const uint8_t* L, const uint8_t* R, bool stagePageable)
 {
     if (int rc = flush_pending_out(c, s)) return rc;
-    if (pageable_direct() || (host_is_pinned(L) && host_is_pinned(R))) {
+    if (!stagePageable || (host_is_pinned(L) && host_is_pinned(R))) {
         CU(cudaMemcpyAsync(s.img[0], L, c->N, cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(s.img[1], R, c->N, cudaMemcpyHostToDevice, s.stream));
         return SGMB_OK;
@@ -688,9 +688,9 @@ static int copy_in(SGMB_Context* c, Slot& s, const uint8_t* L, const uint8_t* R)
 
 // Enqueue the copy of the slot's result to `out`; for pageable `out` the last step (staging -> out) happens in
 // flush_pending_out(), which every path calls before it returns to the caller or reuses the slot.
-static int copy_out(SGMB_Context* c, Slot& s, float* out)
+static int copy_out(SGMB_Context* c, Slot& s, float* out, bool stagePageable)
 {
-    if (pageable_direct() || host_is_pinned(out)) {
+    if (!stagePageable || host_is_pinned(out)) {
         CU(cudaMemcpyAsync(out, frame_result(c, s), c->N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         return SGMB_OK;
     }
@@ -708,9 +708,9 @@ extern "C" int SGMB_Match(SGMB_Context* c, const uint8_t* L, const uint8_t* R, f
     Slot& s = c->slots[0];
     const int rc = [&]() -> int {
         CU(cudaEventRecord(s.evStart, s.stream));
-        if (int rc = copy_in(c, s, L, R)) return rc;
+        if (int rc = copy_in(c, s, L, R, false)) return rc;
         if (int rc = launch_slot_frame(c, s)) return rc;
-        if (out) if (int rc = copy_out(c, s, out)) return rc;
+        if (out) if (int rc = copy_out(c, s, out, false)) return rc;
         CU(cudaEventRecord(s.evStop, s.stream));
         CU(cudaStreamSynchronize(s.stream));
         CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
@@ -764,9 +764,9 @@ static int run_batch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* c
             if (deviceMem) {
                 if (int rc = enqueue_frame(c, s, Ls[k], Rs[k], outs[k], false, nullptr)) return rc;
             } else {
-                if (int rc = copy_in(c, s, Ls[k], Rs[k])) return rc;
+                if (int rc = copy_in(c, s, Ls[k], Rs[k], true)) return rc;
                 if (int rc = launch_slot_frame(c, s)) return rc;
-                if (int rc = copy_out(c, s, outs[k])) return rc;
+                if (int rc = copy_out(c, s, outs[k], true)) return rc;
             }
         }
         for (int j = 1; j < c->nslots; ++j) {

@@ -3,27 +3,30 @@
 //
 // Restates ComputeDisparity() (SemiGlobalMatching.c:374-443, both `inverse` modes) and LRCheck()
 // (SemiGlobalMatching.c:445-470).  S(p,d) = sum_r L_r(p,d) is exactly the reference's cost_aggr after
-// CostAggregation() (SemiGlobalMatching.c:198-221,345); it only ever exists in shared memory unless the taps
-// are enabled, in which case it is also written out in the reference layout [N][D].
+// CostAggregation() (SemiGlobalMatching.c:198-221,345); it only ever exists in registers and shared memory unless the
+// taps are enabled, in which case it is also written out in the reference layout [N][D].
 //
-// The kernel streams 8 (or 4) byte planes once and is meant to run at HBM speed, so the loads of the NEXT tile
-// (128 bytes per thread, straight into the registers phase A has just consumed) are in flight during phase B.
-// One CTA owns one image row and walks it from right to left in tiles of TW columns:
-//   phase A : CPP lanes share a pixel, each owning 16 consecutive disparities (one 128-bit load per plane): add
-//             the planes as packed 16-bit fields (+ the side buffer of irregular paths) and store S into a
-//             shared-memory ring of 2*TW + D columns;
-//   phase B : (after one __syncthreads) half of the CTA scans the LEFT view of the tile's columns, the other half
-//             the RIGHT view of the same number of pixels, those whose first column lies in this tile (the right view
-//             reads the ring along the diagonal S[x + d][d], SemiGlobalMatching.c:397-399; walking right to left, all
-//             later columns of such a pixel are already in the ring).  Four lanes share a pixel; keys
-//             (cost << 16 | d) make "lowest d wins ties" and "second = min over d != best" one integer min / max
-//             each (:390-393,412-419); the four partial results are combined with xor shuffles and parked,
-//             together with the two costs next to the best one, in a 16-byte record per pixel;
-//   epilogue: every thread finishes whole pixels from the records (uniqueness, border, sub-pixel fit), then
-//             LRCheck runs over the row.
-// The ring spans 2*TW + D columns so that phase A of the next tile never overwrites a column phase B still reads:
-// one barrier per tile.  Its row stride (16*CPP + 2 halfwords, an odd number of 32-bit words) spreads row-wise
-// and diagonal accesses over the banks.
+// The kernel streams 8 (or 4) byte planes once and is meant to run at HBM speed.  One CTA owns one image row and walks it
+// from right to left in tiles of TW columns; CPP lanes share a pixel, each owning 16 consecutive disparities (one 128-bit
+// load per plane):
+//   phase A : add the planes as packed 16-bit fields (+ the side buffer of irregular paths); every plane register is
+//             re-loaded for the NEXT tile as soon as it has been consumed, so 128 bytes per thread are always in flight.
+//             The LEFT view is scanned right here, from the registers that hold the sums: keys (S << 4 | index) make
+//             "lowest d wins ties" and "second = min over d != best" (:390-393,412-419) packed 16-bit min / max
+//             (S <= 12 * 255 < 4096), three DPX instructions per two disparities; the CPP partial results are combined with
+//             xor shuffles.  The sums also go to a shared-memory ring, SKEWED so that the right view becomes a row scan
+//             as well: word i of the lane's chunk (disparities 2i, 2i+1 of the chunk) of pixel c goes to ring row c - 2i.
+//   phase B : (after one __syncthreads) the right-view pixel x reads S[x + d][d] (:397-399); with the skew the even
+//             disparities of chunk v lie in ring row x + dmin + 16v and the odd ones in the next row, eight words each -
+//             two 128-bit loads per row and one PRMT per word rebuild the same packed layout the left view scans, and
+//             the same scan code runs on it.  Walking right to left, all columns a right pixel needs have been summed
+//             when its first column's tile is; every tile finishes TW left and TW right pixels.
+//   epilogue: every thread finishes whole pixels from the parked 16-byte records (uniqueness, border, sub-pixel fit),
+//             then LRCheck runs over the row.
+// Cells that do not exist (disparities beyond D in the last chunk, right-view columns beyond the image) hold the marker
+// 0x0FFF, larger than any sum, so they lose every comparison without a test.  The ring has a multiple of TW rows and at
+// least 2*TW + D, so that phase A of the next tile never touches a row phase B still reads (one barrier per tile) and a
+// tile's rows wrap around the ring's end only in one tile out of RB / TW (a separate code path).
 #pragma once
 
 #include <math.h>
@@ -47,31 +50,43 @@ struct WtaParams {
     int W, H, D, Dp, dmin;
     int checkUnique;  float oneMinusRatio;   // (1 - uniqueness_ratio), formed in float like the reference
     int checkLR;      float lrThres;
-    int ringCols;               // 2 * TW + D
+    int ringCols;               // rows of the shared-memory ring: WtaShape<CPP>::ring_rows(D)
 };
 
 __device__ __forceinline__ float sgm_invalid() { return __int_as_float(0x7f800000); }
 
 struct WtaPair { uint32_t kmin, ksec; };   // smallest and second smallest key; key = cost << 16 | disparity index
 
-__device__ __forceinline__ void wta_push2(WtaPair& w, uint32_t ka, uint32_t kb)
+constexpr uint32_t kWtaMissing = 0x0FFFu;  // ring value of a cell that does not exist; every real sum is smaller (<= 12 * 255)
+
+// Smallest and second smallest of the 16 cells of one chunk: w[i] holds the sums of disparity indices d0 + 2i (low half)
+// and d0 + 2i + 1 (high half).  Packed 16-bit keys (sum << 4 | position in the chunk) keep both halves of a register busy;
+// the result is widened to (sum << 16 | disparity index) keys, 0xFFFFFFFF where the chunk has no (further) real cell.
+__device__ __forceinline__ WtaPair wta_scan16(const uint32_t (&w)[8], int d0)
 {
-    const uint32_t lo = min(ka, kb), hi = max(ka, kb);
-    w.ksec = min(min(w.ksec, max(w.kmin, lo)), hi);
-    w.kmin = min(w.kmin, lo);
+    uint32_t m = w[0] * 16u + 0x00010000u, s = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        const uint32_t k = w[i] * 16u + (uint32_t)(2 * i) * 0x00010001u + 0x00010000u;   // fields <= 0x0FFF: no carry between them
+        s = __vminu2(s, __vmaxu2(m, k));
+        m = __vminu2(m, k);
+    }
+    const uint32_t a = m & 0xFFFFu, b = m >> 16;
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    const uint32_t sec = min(hi, min(s & 0xFFFFu, s >> 16));
+    auto widen = [&](uint32_t k16) -> uint32_t {
+        const uint32_t cost = k16 >> 4;
+        return cost >= kWtaMissing ? 0xFFFFFFFFu : (cost << 16) | (uint32_t)(d0 + (int)(k16 & 15u));
+    };
+    return WtaPair{widen(lo), widen(sec)};
 }
 
-__device__ __forceinline__ void wta_push1(WtaPair& w, uint32_t k)
-{
-    w.ksec = min(w.ksec, max(w.kmin, k));
-    w.kmin = min(w.kmin, k);
-}
-
-// combine the partial results of the four lanes that share a pixel (lane ids differ in bits 0 and 1)
-__device__ __forceinline__ void wta_reduce4(WtaPair& w)
+// combine the partial results of the CPP lanes that share a pixel (consecutive lane ids)
+template <int CPP>
+__device__ __forceinline__ void wta_reduce(WtaPair& w)
 {
 #pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
+    for (int o = CPP / 2; o > 0; o >>= 1) {
         const uint32_t k2 = __shfl_xor_sync(0xffffffffu, w.kmin, o), s2 = __shfl_xor_sync(0xffffffffu, w.ksec, o);
         w.ksec = min(min(w.ksec, s2), max(w.kmin, k2));
         w.kmin = min(w.kmin, k2);
@@ -104,18 +119,21 @@ template <int CPP>
 struct WtaShape {
     static constexpr int kThreads = CPP == 16 ? 512 : 256;
     static constexpr int kTW = kThreads / CPP;          // columns per tile
-    static constexpr int kRS = 16 * CPP + 2;            // ring row stride in halfwords
+    static constexpr int kRW = 8 * CPP + 4;             // ring row stride in 32-bit words (a multiple of 4: rows are 16-byte aligned)
+    // ring rows: a multiple of the tile width, at least 2 * TW + D
+    __host__ __device__ static constexpr int ring_rows(int D) { return 2 * kTW + ((D + kTW - 1) / kTW) * kTW; }
+    __host__ __device__ static constexpr size_t ring_bytes(int D) { return (size_t)ring_rows(D) * kRW * 4; }
 };
 
 template <int CPP, int NP, bool TAPS>
 __global__ void __launch_bounds__(WtaShape<CPP>::kThreads, CPP == 16 ? 1 : 3)
 sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 {
-    constexpr int THREADS = WtaShape<CPP>::kThreads, TW = WtaShape<CPP>::kTW, RS = WtaShape<CPP>::kRS;
+    constexpr int THREADS = WtaShape<CPP>::kThreads, TW = WtaShape<CPP>::kTW, RW = WtaShape<CPP>::kRW;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int W = P.W, D = P.D, Dp = P.Dp;
-    const int RB = P.ringCols;                    // 2*TW + D columns
-    uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);
+    const int RB = P.ringCols;                    // ring rows
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
 
     const int y = blockIdx.x;
     const size_t rowBase = (size_t)y * W;
@@ -125,151 +143,155 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
     uint4* recL = P.records + rowBase;
     uint4* recR = P.records + (size_t)P.H * W + rowBase;
 
-    // ---- phase A mapping: (pixel of the tile, 16-disparity chunk)
+    // thread (pix, v): pixel `pix` of the tile (phase A: left image column; phase B: right-view pixel), chunk v of 16 disparities
     const int pix = tid / CPP, v = tid % CPP;
     const bool chunkOk = 16 * v < Dp;             // CPP is the power of two >= Dp / 16
     const uint8_t* srcLane = P.planes + rowBase * Dp + 16 * v;
-    // ---- phase B mapping: first half of the CTA = left view, second half = right view; four lanes per pixel
-    constexpr int HALF = THREADS / 2, GROUPS = HALF / 4;
-    const bool rightRole = tid >= HALF;
-    const int grp = (tid % HALF) / 4, sub = tid % 4;
-    const int CH = (((D + 3) / 4) + 1) & ~1;      // disparities per lane, even
-    const int k0 = sub * CH;                      // this lane scans indices [k0, min(k0 + CH, n))
+    const size_t planeStride = P.planeStride;
+
+    // ---- ring: every cell "missing" until a sum is stored; right pixels without any candidate (x + dmin >= W)
+    for (int i = tid; i < RB * RW; i += THREADS) ring[i] = kWtaMissing * 0x00010001u;
+    if (P.checkLR)
+        for (int x = max(0, W - P.dmin) + tid; x < W; x += THREADS) recR[x] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+
+    // cost of the cell (ring row of its column, disparity index d): row (rc - 2 * ((d >> 1) & 7)) mod RB, word d >> 1, half d & 1
+    auto ring_cost = [&](int rc, int d) -> uint32_t {
+        int r = rc - 2 * ((d >> 1) & 7);
+        if (r >= RB) r -= RB;
+        if (r < 0) r += RB;
+        const uint32_t w = ring[r * RW + (d >> 1)];
+        return (d & 1) ? (w >> 16) : (w & 0xFFFFu);
+    };
 
     uint4 cur[NP];
     int eCur = -1;
-    const size_t planeStride = P.planeStride;
-    auto load_tile = [&](int c0, uint4 (&q)[NP], int& e) {
-        const int c = c0 + pix;
-        e = -1;
+    const int lastStart = ((W - 1) / TW) * TW;    // first tile processed = rightmost; tiles are aligned to TW
+    {
+        const int c = lastStart + pix;
         if (c < W && chunkOk) {
             const uint8_t* src = srcLane + (size_t)c * Dp;
 #pragma unroll
-            for (int r = 0; r < NP; ++r) { q[r] = __ldcs(reinterpret_cast<const uint4*>(src)); src += planeStride; }
-            if (P.hasSide) e = __ldg(P.entryOf + rowBase + c);
+            for (int r = 0; r < NP; ++r) { cur[r] = __ldcs(reinterpret_cast<const uint4*>(src)); src += planeStride; }
+            if (P.hasSide) eCur = __ldg(P.entryOf + rowBase + c);
         }
-    };
+    }
+    __syncthreads();
 
-    // The row is walked from its RIGHT end to the left: a right-view pixel x needs the columns x + dmin .. x + dmin + D - 1,
-    // so with this order it is complete as soon as its own tile has been summed - every tile finishes TW left-view and TW
-    // right-view pixels, and both halves of the CTA have the same amount of work in every tile (walking left to right made
-    // half of the warps idle for the first D columns and left them five tiles' worth of pixels after the last one).
-    const int lastStart = ((W - 1) / TW) * TW;    // first tile processed = rightmost
-    int slotTile = lastStart % RB;                // c0 % RB
-    load_tile(lastStart, cur, eCur);
+    int s0 = lastStart % RB;                      // ring row of column c0 (a multiple of TW)
     for (int c0 = lastStart; c0 >= 0; c0 -= TW) {
         const int cols = min(TW, W - c0);
-        const bool firstTile = (c0 == lastStart);
-        // ------------------------------------------------------------------ phase A
+        // ------------------------------------------------------------------ phase A: plane sum, left view, skewed store
         const int c = c0 + pix;
-        if (c < W && chunkOk) {
+        const bool active = c < W && chunkOk;     // this thread sums a chunk of column c
+        const bool nextOk = c0 > 0 && chunkOk;    // ... and one of column c - TW in the next tile (always inside the row)
+        const int rTop = s0 + pix;                // ring row of column c (< RB: s0 is a multiple of TW)
+        WtaPair wl{0xFFFFFFFFu, 0xFFFFFFFFu};
+        {
+            const uint8_t* nsrc = srcLane + (size_t)(c - TW) * Dp;
             uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};     // even / odd disparities as 16-bit fields
 #pragma unroll
-            for (int r = 0; r < NP; ++r) {
-                const uint32_t w[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
+            for (int r = 0; r < NP; r += 2) {                        // two planes per step: one 3-input add per field pair
+                const uint32_t a[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
+                const uint32_t b[4] = {cur[r + 1].x, cur[r + 1].y, cur[r + 1].z, cur[r + 1].w};
+                // the registers are free: their loads for the next tile fly during the rest of this tile
+                if (nextOk) {
+                    cur[r] = __ldcs(reinterpret_cast<const uint4*>(nsrc + r * planeStride));
+                    cur[r + 1] = __ldcs(reinterpret_cast<const uint4*>(nsrc + (r + 1) * planeStride));
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    ev[i] += w[i] & 0x00FF00FFu;
-                    od[i] += __byte_perm(w[i], 0, 0x4341);
+                    ev[i] = ev[i] + (a[i] & 0x00FF00FFu) + (b[i] & 0x00FF00FFu);
+                    od[i] = od[i] + __byte_perm(a[i], 0, 0x4341) + __byte_perm(b[i], 0, 0x4341);
                 }
             }
-            uint32_t out[8];                                        // natural order: (d0,d1),(d2,d3),...
+            const int eNow = eCur;
+            if (P.hasSide) eCur = nextOk ? __ldg(P.entryOf + rowBase + c - TW) : -1;
+            if (active) {
+                uint32_t out[8];                                    // natural order: (d0,d1),(d2,d3),...
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                out[2 * i] = __byte_perm(ev[i], od[i], 0x5410);
-                out[2 * i + 1] = __byte_perm(ev[i], od[i], 0x7632);
-            }
-            if (eCur >= 0) {
-                const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)eCur * Dp + 16 * v);
-                const uint4 a = __ldg(sp), b = __ldg(sp + 1);
-                out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
-                out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
-            }
-            if (16 * v + 16 > D) {                                  // padding disparities never win
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int d = 16 * v + 2 * i;
-                    if (d >= D) out[i] |= 0x0000FFFFu;
-                    if (d + 1 >= D) out[i] |= 0xFFFF0000u;
+                for (int i = 0; i < 4; ++i) {
+                    out[2 * i] = __byte_perm(ev[i], od[i], 0x5410);
+                    out[2 * i + 1] = __byte_perm(ev[i], od[i], 0x7632);
                 }
-            }
-            int slot = slotTile + pix; if (slot >= RB) slot -= RB;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * RS + 16 * v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = out[i];
-            if (TAPS && P.S) {
-                uint16_t* g = P.S + (rowBase + c) * D + 16 * v;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int d = 16 * v + 2 * i;
-                    if (d < D) g[2 * i] = (uint16_t)(out[i] & 0xFFFFu);
-                    if (d + 1 < D) g[2 * i + 1] = (uint16_t)(out[i] >> 16);
+                if (eNow >= 0) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)eNow * Dp + 16 * v);
+                    const uint4 a = __ldg(sp), b = __ldg(sp + 1);
+                    out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
+                    out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
                 }
-            }
-        }
-        // the loads of the next tile fly during phase B (issued only now: the sums above must not wait on them)
-        if (c0 > 0) load_tile(c0 - TW, cur, eCur);
-        __syncthreads();
-        // ------------------------------------------------------------------ phase B
-        if (!rightRole) {
-            for (int g0 = 0; g0 < cols; g0 += GROUPS) {                // uniform per warp: shuffles inside
-                const int gi = g0 + grp;
-                WtaPair w{0xFFFFFFFFu, 0xFFFFFFFFu};
-                int slot = slotTile + gi; if (slot >= RB) slot -= RB;
-                const uint16_t* row = ring + slot * RS;
-                if (gi < cols) {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(row + k0);
-                    const int n2 = max(0, min(CH, D - k0)) / 2;        // whole pairs; an odd tail is handled below
-#pragma unroll 4
-                    for (int i = 0; i < n2; ++i) {
-                        const uint32_t pr = q[i];
-                        wta_push2(w, pr * 65536u + (uint32_t)(k0 + 2 * i), (pr & 0xFFFF0000u) | (uint32_t)(k0 + 2 * i + 1));
+                if (TAPS && P.S) {
+                    uint16_t* g = P.S + (rowBase + c) * D + 16 * v;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int d = 16 * v + 2 * i;
+                        if (d < D) g[2 * i] = (uint16_t)(out[i] & 0xFFFFu);
+                        if (d + 1 < D) g[2 * i + 1] = (uint16_t)(out[i] >> 16);
                     }
-                    if (k0 + 2 * n2 < min(k0 + CH, D)) wta_push1(w, (uint32_t)row[k0 + 2 * n2] * 65536u + (uint32_t)(k0 + 2 * n2));
                 }
-                wta_reduce4(w);
-                if (sub == 0 && gi < cols) {
-                    const int best = (int)(w.kmin & 0xFFFFu);
-                    const uint32_t c1 = best > 0 ? row[best - 1] : 0u, c2 = best + 1 < D ? row[best + 1] : 0xFFFFu;
-                    recL[c0 + gi] = make_uint4(w.kmin, w.ksec, c1 | (c2 << 16), 0u);
+                if (16 * v + 16 > D) {                              // disparity indices beyond the range do not exist
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int d = 16 * v + 2 * i;
+                        if (d >= D) out[i] = (out[i] & 0xFFFF0000u) | kWtaMissing;
+                        if (d + 1 >= D) out[i] = (out[i] & 0x0000FFFFu) | (kWtaMissing << 16);
+                    }
                 }
-            }
-        } else if (P.checkLR) {
-            // right pixels whose first column x + dmin lies in this tile (all their other columns are further right and
-            // already summed); the rightmost tile also takes the pixels without any candidate (x + dmin >= W)
-            const int rightBegin = max(0, c0 - P.dmin);
-            const int rightEnd = firstTile ? W : min(W, c0 + cols - P.dmin);
-            for (int x0 = rightBegin; x0 < rightEnd; x0 += GROUPS) {
-                const int x = x0 + grp;
-                const int first = x + P.dmin;                         // left column of disparity index 0
-                const int n = (x < rightEnd) ? max(0, min(D, W - first)) : 0;
-                WtaPair w{0xFFFFFFFFu, 0xFFFFFFFFu};
-                int slot0 = slotTile + (first - c0);                  // first % RB; 0 <= first - c0 < TW wherever n > 0
-                slot0 -= (slot0 >= RB) ? RB : 0;
-                {
-                    const int kEnd = min(k0 + CH, n);
-                    int slot = slot0 + k0; if (slot >= RB) slot -= RB;
-                    const int run = min(kEnd - k0, RB - slot);         // elements before the ring wraps
-                    const uint16_t* q = ring + slot * RS + k0;
-                    int i = 0;
-#pragma unroll 4
-                    for (; i < run; ++i) wta_push1(w, (uint32_t)q[i * (RS + 1)] * 65536u + (uint32_t)(k0 + i));
-                    q -= RB * RS;
-                    for (; k0 + i < kEnd; ++i) wta_push1(w, (uint32_t)q[i * (RS + 1)] * 65536u + (uint32_t)(k0 + i));
+                // skewed store: word i of the chunk -> ring row (c - 2i) mod RB, word 8v + i
+                uint32_t* dst = ring + rTop * RW + 8 * v;
+                if (s0 != 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i * (1 - 2 * RW)] = out[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i * (1 - 2 * RW) + (pix < 2 * i ? RB * RW : 0)] = out[i];
                 }
-                wta_reduce4(w);
-                if (sub == 0 && x < rightEnd) {
-                    const int best = (int)(w.kmin & 0xFFFFu);
-                    auto cost = [&](int k) -> uint32_t {
-                        if (k < 0 || k >= n) return 0xFFFFu;
-                        int sl = slot0 + k; if (sl >= RB) sl -= RB;
-                        return ring[sl * RS + k];
-                    };
-                    recR[x] = make_uint4(w.kmin, w.ksec, cost(best - 1) | (cost(best + 1) << 16), 0u);
-                }
+                wl = wta_scan16(out, 16 * v);                       // left view of column c: this chunk, in registers
             }
         }
-        slotTile -= TW; if (slotTile < 0) slotTile += RB;
+        wta_reduce<CPP>(wl);                                        // all lanes (idle ones carry "nothing")
+        __syncwarp();                                               // the pixel's words (written by lanes of this warp) are visible
+        {
+            // costs next to the best disparity (sub-pixel fit): lane v = 0 fetches S[best - 1], lane v = 1 (or 0 again when
+            // the pixel has one lane) S[best + 1] - one ring read per lane, side by side instead of one after the other
+            const int best = (int)(wl.kmin & 0xFFFFu);
+            const int k = best + (CPP > 1 && v == 1 ? 1 : -1);
+            uint32_t nb = (k < 0) ? 0u : (k >= D ? 0xFFFFu : ((active && v < 2) ? ring_cost(rTop, k) : 0u));
+            uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : (best + 1 < D ? ring_cost(rTop, best + 1) : 0xFFFFu);
+            if (active && v == 0) recL[c] = make_uint4(wl.kmin, wl.ksec, nb | (c2 << 16), 0u);
+        }
+        __syncthreads();
+        // ------------------------------------------------------------------ phase B: right view of the pixels whose first column lies in this tile
+        if (P.checkLR) {
+            const int x = c - P.dmin;                               // c = x + dmin: left column of disparity index 0
+            const bool scan = pix < cols && x >= 0 && chunkOk;
+            WtaPair wr{0xFFFFFFFFu, 0xFFFFFFFFu};
+            if (scan) {
+                int r = rTop + 16 * v;                              // even disparities of chunk v: ring row of column c + 16v, odd ones: the next row
+                if (r >= RB) r -= RB;
+                const int r1 = r + 1 == RB ? 0 : r + 1;
+                const uint4* pe = reinterpret_cast<const uint4*>(ring + r * RW + 8 * v);
+                const uint4* po = reinterpret_cast<const uint4*>(ring + r1 * RW + 8 * v);
+                const uint4 e0 = pe[0], e1 = pe[1], o0 = po[0], o1 = po[1];
+                const uint32_t wv[8] = {__byte_perm(e0.x, o0.x, 0x7610), __byte_perm(e0.y, o0.y, 0x7610), __byte_perm(e0.z, o0.z, 0x7610),
+                                        __byte_perm(e0.w, o0.w, 0x7610), __byte_perm(e1.x, o1.x, 0x7610), __byte_perm(e1.y, o1.y, 0x7610),
+                                        __byte_perm(e1.z, o1.z, 0x7610), __byte_perm(e1.w, o1.w, 0x7610)};
+                wr = wta_scan16(wv, 16 * v);
+            }
+            wta_reduce<CPP>(wr);
+            {
+                const int best = (int)(wr.kmin & 0xFFFFu);
+                auto cost = [&](int k) -> uint32_t {                // 65535 where the reference sees UINT16_MAX (k outside the candidates)
+                    if (k < 0 || k >= D) return 0xFFFFu;
+                    const uint32_t cst = ring_cost(rTop + k, k);
+                    return cst == kWtaMissing ? 0xFFFFu : cst;
+                };
+                const int k = best + (CPP > 1 && v == 1 ? 1 : -1);
+                const uint32_t nb = (scan && v < 2) ? cost(k) : 0u;
+                const uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : (scan ? cost(best + 1) : 0u);
+                if (scan && v == 0) recR[x] = make_uint4(wr.kmin, wr.ksec, nb | (c2 << 16), 0u);
+            }
+        }
+        s0 -= TW; if (s0 < 0) s0 += RB;
     }
     // ---------------------------------------------------------------------- finish whole pixels from the records
     __syncthreads();
