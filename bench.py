@@ -212,6 +212,15 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # host-side barrier (gloo): ranks that wait while rank 0 drives ALL GPUs through the library's pool must not spin in a
+    # NCCL kernel on their own GPU - that kernel would time-slice with rank 0's work there
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -377,10 +386,10 @@ def main() -> int:
     #      one context per device, no inter-GPU communication); rank 0 only, after the per-rank sections
     pool_c4 = None
     if args.pool_pairs > 0:
-        barrier()
+        host_barrier()
         if rank == 0:
             pool_c4 = bench_pool_c4(sgm, torch, args.pool_pairs, args.inflight, de_per_frame)
-        barrier()
+        host_barrier()
     clocks = sampler.stop()
 
     if rank == 0:
