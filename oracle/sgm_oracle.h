@@ -6,7 +6,7 @@
  * call it, and there only as the checker / the reported CPU baseline.
  *
  * Reference = /root/reference/SemiGlobalMatching/SemiGlobalMatching/SemiGlobalMatching.c
- * (abbreviated SGM.c below).  Parity status: PINNED -- tests/test_oracle_vs_ref.py checks every
+ * (abbreviated SGM.c below).  Parity status: PINNED -- tests/test_oracle_golden.py checks every
  * stage of this restatement against the reference source itself, compiled verbatim by
  * oracle/build_ref.py into oracle/_ref/ (guard rows + padded inputs), and against the
  * committed fixtures in tests/golden/ that were generated from that build.
