@@ -321,6 +321,9 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->padF = ((option->min_disparity + 64 * c->NR + 8) + 3) & ~3;
     c->copyStride = ((size_t)c->padF + c->N + 16 + 3) & ~(size_t)3;
     c->planeStride = c->N * (size_t)c->Dp;
+    // K3 addresses the planes with 32-bit indices in 16-byte units (wta.cuh)
+    if (7 * (c->planeStride >> 4) >= ((size_t)1 << 32))
+        return fail(SGMB_E_UNSUPPORTED, "frame too large: width * height * disparity range must stay below 9.8e9");
     const int W = c->W, H = c->H;
 
     // ---- K3 launch shape

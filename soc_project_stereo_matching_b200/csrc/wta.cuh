@@ -61,7 +61,8 @@ constexpr uint32_t kWtaMissing = 0x0FFFu;  // ring value of a cell that does not
 
 // Smallest and second smallest of the 16 cells of one chunk: w[i] holds the sums of disparity indices d0 + 2i (low half)
 // and d0 + 2i + 1 (high half).  Packed 16-bit keys (sum << 4 | position in the chunk) keep both halves of a register busy;
-// the result is widened to (sum << 16 | disparity index) keys, 0xFFFFFFFF where the chunk has no (further) real cell.
+// the result is widened to (sum << 16 | disparity index) keys; a cell that does not exist keeps the marker as its sum, which
+// still loses against every real cell (wta_finish turns it into the reference's UINT16_MAX).
 __device__ __forceinline__ WtaPair wta_scan16(const uint32_t (&w)[8], int d0)
 {
     uint32_t m = w[0] * 16u + 0x00010000u, s = 0xFFFFFFFFu;
@@ -74,10 +75,8 @@ __device__ __forceinline__ WtaPair wta_scan16(const uint32_t (&w)[8], int d0)
     const uint32_t a = m & 0xFFFFu, b = m >> 16;
     const uint32_t lo = min(a, b), hi = max(a, b);
     const uint32_t sec = min(hi, min(s & 0xFFFFu, s >> 16));
-    auto widen = [&](uint32_t k16) -> uint32_t {
-        const uint32_t cost = k16 >> 4;
-        return cost >= kWtaMissing ? 0xFFFFFFFFu : (cost << 16) | (uint32_t)(d0 + (int)(k16 & 15u));
-    };
+    // (sum << 4 | i) -> (sum << 16 | d0 + i) = k * 4096 + d0 - 4095 * i: one AND and two multiply-adds
+    auto widen = [&](uint32_t k16) -> uint32_t { return (k16 * 4096u + (uint32_t)d0) - 4095u * (k16 & 15u); };
     return WtaPair{widen(lo), widen(sec)};
 }
 
@@ -100,8 +99,9 @@ __device__ __forceinline__ float wta_finish(uint4 rec, int D, int dmin, int chec
 {
     const int best = (int)(rec.x & 0xFFFFu);
     const int cmin = (int)(rec.x >> 16);
-    const int second = (int)(rec.y >> 16);
-    if (cmin == 0xFFFF) return sgm_invalid();          // no candidate at all (right view, x + dmin >= W)
+    int second = (int)(rec.y >> 16);
+    if (cmin >= (int)kWtaMissing) return sgm_invalid();   // no candidate at all (right view, x + dmin >= W)
+    if (second >= (int)kWtaMissing) second = 0xFFFF;      // a single candidate: the reference's second minimum stays UINT16_MAX (:381)
     if (checkUnique) {
         const float lim = __fmul_rn((float)cmin, oneMinusRatio);
         const int ilim = (int)(__float2uint_rz(lim) & 0xFFFFu);            // (uint16_t)(min * (1 - ratio))  :422
@@ -113,6 +113,15 @@ __device__ __forceinline__ float wta_finish(uint4 rec, int D, int dmin, int chec
     int denom = (int)(int16_t)(c1 + c2 - 2 * cmin);                        // :437
     if (denom < 1) denom = 1;
     return __fadd_rn((float)(best + dmin), __fdiv_rn((float)(c1 - c2), __fmul_rn((float)denom, 2.0f)));   // :440
+}
+
+// base + 16 * idx with a 32-bit index: one IMAD.WIDE (left to itself the compiler widens every term of the index to 64 bits
+// first, four instructions per address)
+__device__ __forceinline__ const uint4* wta_chunk_ptr(const uint4* base, uint32_t idx)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(idx), "l"((unsigned long long)base));
+    return reinterpret_cast<const uint4*>(a);
 }
 
 template <int CPP>
@@ -146,21 +155,30 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
     // thread (pix, v): pixel `pix` of the tile (phase A: left image column; phase B: right-view pixel), chunk v of 16 disparities
     const int pix = tid / CPP, v = tid % CPP;
     const bool chunkOk = 16 * v < Dp;             // CPP is the power of two >= Dp / 16
-    const uint8_t* srcLane = P.planes + rowBase * Dp + 16 * v;
-    const size_t planeStride = P.planeStride;
+    // plane r, column c, this lane's chunk = rowChunks[c * dp16 + r * ps16] in 16-byte units: 32-bit indices (the host
+    // refuses frames with 7 * planeStride / 16 >= 2^32), one multiply-add per load address
+    const uint4* rowChunks = reinterpret_cast<const uint4*>(P.planes + rowBase * Dp) + v;
+    const uint32_t dp16 = (uint32_t)Dp >> 4, ps16 = (uint32_t)(P.planeStride >> 4);
 
     // ---- ring: every cell "missing" until a sum is stored; right pixels without any candidate (x + dmin >= W)
     for (int i = tid; i < RB * RW; i += THREADS) ring[i] = kWtaMissing * 0x00010001u;
     if (P.checkLR)
         for (int x = max(0, W - P.dmin) + tid; x < W; x += THREADS) recR[x] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
 
-    // cost of the cell (ring row of its column, disparity index d): row (rc - 2 * ((d >> 1) & 7)) mod RB, word d >> 1, half d & 1
+    // cost of the cell (ring row rc of its column - may exceed RB by less than RB -, disparity index d in [0, D)):
+    // row (rc - 2 * ((d >> 1) & 7)) mod RB, word d >> 1, half d & 1.  Branch-free: every lane of the warp calls it.
     auto ring_cost = [&](int rc, int d) -> uint32_t {
         int r = rc - 2 * ((d >> 1) & 7);
-        if (r >= RB) r -= RB;
-        if (r < 0) r += RB;
-        const uint32_t w = ring[r * RW + (d >> 1)];
-        return (d & 1) ? (w >> 16) : (w & 0xFFFFu);
+        r -= r >= RB ? RB : 0;
+        r += r < 0 ? RB : 0;
+        return __byte_perm(ring[r * RW + (d >> 1)], 0u, (d & 1) ? 0x4432u : 0x4410u);
+    };
+    // the same for a neighbour k of the best index that may lie outside [0, D): `below` / `above` are what the reference's
+    // cost_local holds there (:433-435 read index -1 / D only for pixels that were already declared invalid)
+    auto neighbour_cost = [&](int rc0, bool rowFollowsIndex, int k) -> uint32_t {
+        const int kc = min(max(k, 0), D - 1);
+        const uint32_t cst = ring_cost(rowFollowsIndex ? rc0 + kc : rc0, kc);
+        return (unsigned)k >= (unsigned)D ? 0xFFFFu : cst;
     };
 
     uint4 cur[NP];
@@ -169,9 +187,9 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
     {
         const int c = lastStart + pix;
         if (c < W && chunkOk) {
-            const uint8_t* src = srcLane + (size_t)c * Dp;
+            const uint32_t src = (uint32_t)c * dp16;
 #pragma unroll
-            for (int r = 0; r < NP; ++r) { cur[r] = __ldcs(reinterpret_cast<const uint4*>(src)); src += planeStride; }
+            for (int r = 0; r < NP; ++r) cur[r] = __ldcs(wta_chunk_ptr(rowChunks, src + (uint32_t)r * ps16));
             if (P.hasSide) eCur = __ldg(P.entryOf + rowBase + c);
         }
     }
@@ -187,21 +205,22 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
         const int rTop = s0 + pix;                // ring row of column c (< RB: s0 is a multiple of TW)
         WtaPair wl{0xFFFFFFFFu, 0xFFFFFFFFu};
         {
-            const uint8_t* nsrc = srcLane + (size_t)(c - TW) * Dp;
+            const uint32_t nsrc = (uint32_t)(nextOk ? c - TW : 0) * dp16;
             uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};     // even / odd disparities as 16-bit fields
 #pragma unroll
             for (int r = 0; r < NP; r += 2) {                        // two planes per step: one 3-input add per field pair
                 const uint32_t a[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
                 const uint32_t b[4] = {cur[r + 1].x, cur[r + 1].y, cur[r + 1].z, cur[r + 1].w};
-                // the registers are free: their loads for the next tile fly during the rest of this tile
-                if (nextOk) {
-                    cur[r] = __ldcs(reinterpret_cast<const uint4*>(nsrc + r * planeStride));
-                    cur[r + 1] = __ldcs(reinterpret_cast<const uint4*>(nsrc + (r + 1) * planeStride));
-                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     ev[i] = ev[i] + (a[i] & 0x00FF00FFu) + (b[i] & 0x00FF00FFu);
                     od[i] = od[i] + __byte_perm(a[i], 0, 0x4341) + __byte_perm(b[i], 0, 0x4341);
+                }
+                // the registers are free now: their loads for the next tile fly during the rest of this tile (issued after
+                // the adds so that the old values need no copies)
+                if (nextOk) {
+                    cur[r] = __ldcs(wta_chunk_ptr(rowChunks, nsrc + (uint32_t)r * ps16));
+                    cur[r + 1] = __ldcs(wta_chunk_ptr(rowChunks, nsrc + (uint32_t)(r + 1) * ps16));
                 }
             }
             const int eNow = eCur;
@@ -249,14 +268,15 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
             }
         }
         wta_reduce<CPP>(wl);                                        // all lanes (idle ones carry "nothing")
-        __syncwarp();                                               // the pixel's words (written by lanes of this warp) are visible
-        {
-            // costs next to the best disparity (sub-pixel fit): lane v = 0 fetches S[best - 1], lane v = 1 (or 0 again when
-            // the pixel has one lane) S[best + 1] - one ring read per lane, side by side instead of one after the other
+        // Costs next to the best disparity (sub-pixel fit).  With four or more lanes per pixel and the right view enabled
+        // both views fetch theirs side by side after phase B (lanes v = 0, 1: left view, v = 2, 3: right view); otherwise
+        // lane v = 0 fetches S[best - 1] and lane v = 1 (or 0 again when the pixel has one lane) S[best + 1] right here.
+        constexpr bool kMergedFetch = CPP >= 4;
+        if (!(kMergedFetch && P.checkLR)) {
+            __syncwarp();                                           // the pixel's words (written by lanes of this warp) are visible
             const int best = (int)(wl.kmin & 0xFFFFu);
-            const int k = best + (CPP > 1 && v == 1 ? 1 : -1);
-            uint32_t nb = (k < 0) ? 0u : (k >= D ? 0xFFFFu : ((active && v < 2) ? ring_cost(rTop, k) : 0u));
-            uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : (best + 1 < D ? ring_cost(rTop, best + 1) : 0xFFFFu);
+            const uint32_t nb = neighbour_cost(rTop, false, best + (CPP > 1 && v == 1 ? 1 : -1));
+            const uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : neighbour_cost(rTop, false, best + 1);
             if (active && v == 0) recL[c] = make_uint4(wl.kmin, wl.ksec, nb | (c2 << 16), 0u);
         }
         __syncthreads();
@@ -278,16 +298,23 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
                 wr = wta_scan16(wv, 16 * v);
             }
             wta_reduce<CPP>(wr);
-            {
+            // 65535 where the reference sees UINT16_MAX: index outside the range or column x + k beyond the image (:407);
+            // a left-view cell with k in [0, D) is never the marker
+            auto cost = [&](bool right, int k) -> uint32_t {
+                const uint32_t cst = neighbour_cost(rTop, right, k);
+                return cst == kWtaMissing ? 0xFFFFu : cst;
+            };
+            if (kMergedFetch) {
+                const bool right = (v & 2) != 0;
+                const uint32_t kmin = right ? wr.kmin : wl.kmin, ksec = right ? wr.ksec : wl.ksec;
+                const uint32_t nb = cost(right, (int)(kmin & 0xFFFFu) + ((v & 1) ? 1 : -1));
+                const uint32_t c2 = __shfl_down_sync(0xffffffffu, nb, 1);
+                uint4* rec = (v == 0 && active) ? recL + c : ((v == 2 && scan) ? recR + x : nullptr);
+                if (rec) *rec = make_uint4(kmin, ksec, nb | (c2 << 16), 0u);
+            } else {
                 const int best = (int)(wr.kmin & 0xFFFFu);
-                auto cost = [&](int k) -> uint32_t {                // 65535 where the reference sees UINT16_MAX (k outside the candidates)
-                    if (k < 0 || k >= D) return 0xFFFFu;
-                    const uint32_t cst = ring_cost(rTop + k, k);
-                    return cst == kWtaMissing ? 0xFFFFu : cst;
-                };
-                const int k = best + (CPP > 1 && v == 1 ? 1 : -1);
-                const uint32_t nb = (scan && v < 2) ? cost(k) : 0u;
-                const uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : (scan ? cost(best + 1) : 0u);
+                const uint32_t nb = cost(true, best + (CPP > 1 && v == 1 ? 1 : -1));
+                const uint32_t c2 = CPP > 1 ? __shfl_down_sync(0xffffffffu, nb, 1) : cost(true, best + 1);
                 if (scan && v == 0) recR[x] = make_uint4(wr.kmin, wr.ksec, nb | (c2 << 16), 0u);
             }
         }
