@@ -196,6 +196,7 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
     __syncthreads();
 
     int s0 = lastStart % RB;                      // ring row of column c0 (a multiple of TW)
+    uint32_t nsrc = (uint32_t)(lastStart + pix) * dp16;
     for (int c0 = lastStart; c0 >= 0; c0 -= TW) {
         const int cols = min(TW, W - c0);
         // ------------------------------------------------------------------ phase A: plane sum, left view, skewed store
@@ -205,15 +206,17 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
         const int rTop = s0 + pix;                // ring row of column c (< RB: s0 is a multiple of TW)
         WtaPair wl{0xFFFFFFFFu, 0xFFFFFFFFu};
         {
-            const uint32_t nsrc = (uint32_t)(nextOk ? c - TW : 0) * dp16;
-            uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};     // even / odd disparities as 16-bit fields
+            nsrc -= (uint32_t)TW * dp16;                              // index of column c - TW (unused, and possibly wrapped, when !nextOk)
+            // od: the odd disparities of a word as 16-bit fields (one PRMT per plane); all: the plain 32-bit sum of the words,
+            // = even fields + 256 * odd fields (mod 2^32), so the even fields cost no extraction per plane at all
+            uint32_t all[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int r = 0; r < NP; r += 2) {                        // two planes per step: one 3-input add per field pair
                 const uint32_t a[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
                 const uint32_t b[4] = {cur[r + 1].x, cur[r + 1].y, cur[r + 1].z, cur[r + 1].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    ev[i] = ev[i] + (a[i] & 0x00FF00FFu) + (b[i] & 0x00FF00FFu);
+                    all[i] = all[i] + a[i] + b[i];
                     od[i] = od[i] + __byte_perm(a[i], 0, 0x4341) + __byte_perm(b[i], 0, 0x4341);
                 }
                 // the registers are free now: their loads for the next tile fly during the rest of this tile (issued after
@@ -229,8 +232,9 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
                 uint32_t out[8];                                    // natural order: (d0,d1),(d2,d3),...
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    out[2 * i] = __byte_perm(ev[i], od[i], 0x5410);
-                    out[2 * i + 1] = __byte_perm(ev[i], od[i], 0x7632);
+                    const uint32_t ev = all[i] - (od[i] << 8);       // both even fields <= 8 * 255: exact mod 2^32
+                    out[2 * i] = __byte_perm(ev, od[i], 0x5410);
+                    out[2 * i + 1] = __byte_perm(ev, od[i], 0x7632);
                 }
                 if (eNow >= 0) {
                     const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)eNow * Dp + 16 * v);
