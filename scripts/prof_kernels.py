@@ -87,6 +87,9 @@ print(np.median(ts) * 1e3, np.percentile(ts, 95) * 1e3)
 
 
 if __name__ == "__main__":
+    for a in sys.argv[1:]:                       # ad-hoc shapes: WxHxDxP
+        if a.count("x") == 3:
+            CONFIGS[a] = tuple(int(v) for v in a.split("x"))
     names = [a for a in sys.argv[1:] if a in CONFIGS] or ["c2", "c2p4", "c1", "c3"]
     for nme in names:
         kernels(nme)

@@ -72,6 +72,8 @@ struct Slot {
     float* dispLR = nullptr;
     float* rightRow = nullptr;        // K3 scratch: right-view disparities
     uint4* wtaRecords = nullptr;      // K3 scratch: [2][N] parked scan results
+    int* wtaRowDone = nullptr;        // K3: arrival counters of rows split over several blocks (zero between launches)
+    int* wtaSched = nullptr;          // K3: per-SM block counters + work tickets (zero between launches)
     float* dispSpeckle = nullptr;
     float* dispFinal = nullptr;
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
@@ -122,6 +124,10 @@ struct SGMB_Context {
     // K3 launch shape: lanes per pixel (power of two >= Dp / 16), columns per tile, dynamic shared memory
     int wtaCPP = 8, wtaTW = 32, wtaRingRows = 0;
     size_t wtaSmem = 0;
+    int smCount = 148;
+    int wtaRowsPerSm = 0;
+    int wtaFullRows = 0, wtaPieces = 0;   // K3 work split (wta_plan): whole-row blocks + pieces of the last partial wave of rows
+    int4* wtaSegments = nullptr;
     // L2 flush scratch for SGMB_TimeDevice
     uint8_t* flushBuf = nullptr;
     size_t flushBytes = 0;
@@ -153,16 +159,16 @@ static void free_slot_buffers(Slot& s)
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
     cudaFree(s.pixL); s.pixL = nullptr;
     cudaFree(s.medianScratch); s.medianScratch = nullptr;
-    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords);
+    cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords); cudaFree(s.wtaRowDone); cudaFree(s.wtaSched);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
-    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr;
+    s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr; s.wtaRowDone = nullptr; s.wtaSched = nullptr;
 }
 
 static void free_config(SGMB_Context* c)
 {
     for (auto& s : c->slots) free_slot_buffers(s);
-    cudaFree(c->work); cudaFree(c->entryOf);
-    c->work = nullptr; c->entryOf = nullptr;
+    cudaFree(c->work); cudaFree(c->entryOf); cudaFree(c->wtaSegments);
+    c->work = nullptr; c->entryOf = nullptr; c->wtaSegments = nullptr;
     c->configured = false; c->tapsAllocated = false;
 }
 
@@ -186,6 +192,7 @@ extern "C" int SGMB_Create(SGMB_Context** out, int device, int slots)
     if (prop.major < 10) return fail(SGMB_E_CUDA, "SGMB_Create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     auto* c = new SGMB_Context();
     c->device = device;
+    c->smCount = prop.multiProcessorCount;
     c->nslots = slots;
     c->slots.resize(slots);
     const int rc = [&]() -> int {
@@ -294,6 +301,41 @@ static int wta_prepare(SGMB_Context* c)
     return SGMB_OK;
 }
 
+// K3 work split.  One block per row leaves the SMs unevenly loaded when H is a small, non-integral multiple of the SM count
+// (375 rows on 148 SMs: 79 SMs sum three rows, 69 two, and the kernel takes as long as 444 rows would).  The rows of the
+// last partial wave are therefore cut, as one strip of tiles, into one equal piece per SM; a piece is at most two segments
+// (it may cross one row boundary), launched after the whole-row blocks.  A segment pays for the D - 1 halo columns to its
+// right (plane sum only), so rows are only split when a piece is at least twice as long as its halo.
+static int wta_plan(SGMB_Context* c)
+{
+    const char* sms = getenv("SGM_B200_DEBUG_WTA_SMS");         // tests: plan as if the device had this many SMs
+    const int W = c->W, H = c->H, TW = c->wtaTW, S = std::max(1, sms && atoi(sms) > 0 ? atoi(sms) : c->smCount);
+    const int waves = H / S, rem = H % S;
+    const int nT = (W + TW - 1) / TW, haloT = (c->D - 1 + TW - 1) / TW;
+    c->wtaFullRows = H; c->wtaPieces = 0;
+    const char* e = getenv("SGM_B200_DEBUG_NOSPLIT");
+    if (rem == 0 || waves >= 8 || (e && atoi(e))) return SGMB_OK;
+    const int total = rem * nT, q = (total + S - 1) / S;
+    if (q < 2 * haloT || q < 2) return SGMB_OK;
+    const int pieces = (total + q - 1) / q, first = H - rem;
+    std::vector<int4> seg(2 * (size_t)pieces, make_int4(-1, 0, 0, 0));
+    std::vector<int> perRow(rem, 0);
+    for (int pass = 0; pass < 2; ++pass)
+        for (int p = 0; p < pieces; ++p) {
+            const int t0 = p * q, t1 = std::min(total, t0 + q);
+            int k = 0;
+            for (int r = t0 / nT; r <= (t1 - 1) / nT; ++r, ++k) {
+                const int a = std::max(t0, r * nT) - r * nT, b = std::min(t1, (r + 1) * nT) - r * nT;   // tiles [a, b) of strip row r
+                if (pass == 0) ++perRow[r];
+                else seg[2 * p + k] = make_int4(first + r, a * TW, std::min(W, b * TW), perRow[r]);
+            }
+        }
+    CU(cudaMalloc(&c->wtaSegments, seg.size() * sizeof(int4)));
+    CU(cudaMemcpy(c->wtaSegments, seg.data(), seg.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    c->wtaFullRows = first; c->wtaPieces = pieces; c->wtaRowsPerSm = waves;
+    return SGMB_OK;
+}
+
 extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, const SGMOption* option)
 {
     if (!c) return fail(SGMB_E_ARG, "SGMB_Configure: NULL context");
@@ -335,6 +377,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         else if (chunks <= 4) rc = wta_prepare<4>(c);
         else if (chunks <= 8) rc = wta_prepare<8>(c);
         else                  rc = wta_prepare<16>(c);
+        if (rc == SGMB_OK) rc = wta_plan(c);
         if (rc) return rc;
     }
 
@@ -422,6 +465,10 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.dispLR, c->N * sizeof(float)));
         CU(cudaMalloc(&s.rightRow, c->N * sizeof(float)));
         CU(cudaMalloc(&s.wtaRecords, 2 * c->N * sizeof(uint4)));
+        CU(cudaMalloc(&s.wtaRowDone, (size_t)H * sizeof(int)));
+        CU(cudaMemset(s.wtaRowDone, 0, (size_t)H * sizeof(int)));
+        CU(cudaMalloc(&s.wtaSched, kWtaSchedInts * sizeof(int)));
+        CU(cudaMemset(s.wtaSched, 0, kWtaSchedInts * sizeof(int)));
         CU(cudaMalloc(&s.dispSpeckle, c->N * sizeof(float)));
         CU(cudaMalloc(&s.dispFinal, c->N * sizeof(float)));
         CU(cudaMalloc(&s.labels, 2 * c->N * sizeof(int32_t)));
@@ -570,13 +617,16 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.ringCols = c->wtaRingRows;
         p.rightRow = s.rightRow;
         p.records = s.wtaRecords;
+        p.fullRows = c->wtaFullRows; p.segments = c->wtaSegments; p.rowDone = s.wtaRowDone;
+        p.rowsPerSm = c->wtaRowsPerSm; p.pieces = c->wtaPieces; p.sched = s.wtaSched;
+        const int wtaGrid = c->wtaFullRows + c->wtaPieces;
 #define SGM_WTA_LAUNCH(CPP)                                                                                          \
     if (c->nDirs == 8) {                                                                                             \
-        if (taps) sgm_reduce_wta_lr<CPP, 8, true><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
-        else      sgm_reduce_wta_lr<CPP, 8, false><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
+        if (taps) sgm_reduce_wta_lr<CPP, 8, true><<<wtaGrid, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
+        else      sgm_reduce_wta_lr<CPP, 8, false><<<wtaGrid, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
     } else {                                                                                                         \
-        if (taps) sgm_reduce_wta_lr<CPP, 4, true><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
-        else      sgm_reduce_wta_lr<CPP, 4, false><<<H, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
+        if (taps) sgm_reduce_wta_lr<CPP, 4, true><<<wtaGrid, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);          \
+        else      sgm_reduce_wta_lr<CPP, 4, false><<<wtaGrid, WtaShape<CPP>::kThreads, c->wtaSmem, s.stream>>>(p);         \
     }
         switch (c->wtaCPP) {
             case 1:  SGM_WTA_LAUNCH(1); break;

@@ -51,7 +51,19 @@ struct WtaParams {
     int checkUnique;  float oneMinusRatio;   // (1 - uniqueness_ratio), formed in float like the reference
     int checkLR;      float lrThres;
     int ringCols;               // rows of the shared-memory ring: WtaShape<CPP>::ring_rows(D)
+    // work split (host: wta_plan): blocks [0, fullRows) own one whole row each; block fullRows + p owns piece p = up to two
+    // segments of the remaining rows, so that the last partial wave of rows is spread evenly over all SMs
+    int fullRows;
+    const int4* segments;       // [2 * pieces] {row, colBegin (multiple of TW), colEnd, segments of that row}; row < 0: none
+    int* rowDone;               // [H] arrival counters of the split rows (zero between launches: the last arrival resets)
+    // Which block takes what is decided when the block starts, from the SM it landed on: the first rowsPerSm blocks of an SM
+    // take whole rows, the next one a piece (falling back to the other kind when one has run out), so that every SM ends up
+    // with the same amount of work wherever the hardware places the blocks.  Zero between launches (the last block resets).
+    int rowsPerSm, pieces;
+    int* sched;                 // [kWtaSchedInts]: blocks seen per SM [kWtaSchedSms], row ticket, piece ticket, blocks done
 };
+
+constexpr int kWtaSchedSms = 1024, kWtaSchedInts = kWtaSchedSms + 3;
 
 __device__ __forceinline__ float sgm_invalid() { return __int_as_float(0x7f800000); }
 
@@ -134,17 +146,15 @@ struct WtaShape {
     __host__ __device__ static constexpr size_t ring_bytes(int D) { return (size_t)ring_rows(D) * kRW * 4; }
 };
 
+// One segment [colBegin, colEnd) of row y (the whole row when rowSegs == 1): left-view pixels of these columns, right-view
+// pixels whose first candidate column lies in them.  A segment that does not end at the row's end first sums the D - 1 columns
+// to its right into the ring ("halo" tiles: plane sum + store only), which is all the right view needs from them.
 template <int CPP, int NP, bool TAPS>
-__global__ void __launch_bounds__(WtaShape<CPP>::kThreads, CPP == 16 ? 1 : 3)
-sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
+__device__ __forceinline__ void wta_segment(const WtaParams& P, uint32_t* ring, const int y, const int colBegin, const int colEnd, const int rowSegs)
 {
     constexpr int THREADS = WtaShape<CPP>::kThreads, TW = WtaShape<CPP>::kTW, RW = WtaShape<CPP>::kRW;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int W = P.W, D = P.D, Dp = P.Dp;
     const int RB = P.ringCols;                    // ring rows
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
-
-    const int y = blockIdx.x;
     const size_t rowBase = (size_t)y * W;
     const int tid = threadIdx.x;
     float* rowL = P.dispOut + rowBase;
@@ -162,7 +172,7 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 
     // ---- ring: every cell "missing" until a sum is stored; right pixels without any candidate (x + dmin >= W)
     for (int i = tid; i < RB * RW; i += THREADS) ring[i] = kWtaMissing * 0x00010001u;
-    if (P.checkLR)
+    if (P.checkLR && colEnd == W)
         for (int x = max(0, W - P.dmin) + tid; x < W; x += THREADS) recR[x] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
 
     // cost of the cell (ring row rc of its column - may exceed RB by less than RB -, disparity index d in [0, D)):
@@ -183,7 +193,8 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 
     uint4 cur[NP];
     int eCur = -1;
-    const int lastStart = ((W - 1) / TW) * TW;    // first tile processed = rightmost; tiles are aligned to TW
+    const int haloEnd = min(W, colEnd + D - 1);   // columns [colEnd, haloEnd): summed for the right view only
+    const int lastStart = ((haloEnd - 1) / TW) * TW;   // first tile processed = rightmost; tiles are aligned to TW
     {
         const int c = lastStart + pix;
         if (c < W && chunkOk) {
@@ -197,12 +208,13 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 
     int s0 = lastStart % RB;                      // ring row of column c0 (a multiple of TW)
     uint32_t nsrc = (uint32_t)(lastStart + pix) * dp16;
-    for (int c0 = lastStart; c0 >= 0; c0 -= TW) {
+    for (int c0 = lastStart; c0 >= colBegin; c0 -= TW) {
         const int cols = min(TW, W - c0);
+        const bool halo = c0 >= colEnd;           // block-uniform
         // ------------------------------------------------------------------ phase A: plane sum, left view, skewed store
         const int c = c0 + pix;
         const bool active = c < W && chunkOk;     // this thread sums a chunk of column c
-        const bool nextOk = c0 > 0 && chunkOk;    // ... and one of column c - TW in the next tile (always inside the row)
+        const bool nextOk = c0 > colBegin && chunkOk;   // ... and one of column c - TW in the next tile (always inside the row)
         const int rTop = s0 + pix;                // ring row of column c (< RB: s0 is a multiple of TW)
         WtaPair wl{0xFFFFFFFFu, 0xFFFFFFFFu};
         {
@@ -242,7 +254,7 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
                     out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
                     out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
                 }
-                if (TAPS && P.S) {
+                if (TAPS && P.S && !halo) {
                     uint16_t* g = P.S + (rowBase + c) * D + 16 * v;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -268,8 +280,12 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i * (1 - 2 * RW) + (pix < 2 * i ? RB * RW : 0)] = out[i];
                 }
-                wl = wta_scan16(out, 16 * v);                       // left view of column c: this chunk, in registers
+                if (!halo) wl = wta_scan16(out, 16 * v);            // left view of column c: this chunk, in registers
             }
+        }
+        if (halo) {                                                 // nobody reads the ring before the segment's first real tile
+            s0 -= TW; if (s0 < 0) s0 += RB;
+            continue;
         }
         wta_reduce<CPP>(wl);                                        // all lanes (idle ones carry "nothing")
         // Costs next to the best disparity (sub-pixel fit).  With four or more lanes per pixel and the right view enabled
@@ -326,33 +342,100 @@ sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
     }
     // ---------------------------------------------------------------------- finish whole pixels from the records
     __syncthreads();
-    for (int x = tid; x < W; x += THREADS) {
+    for (int x = colBegin + tid; x < colEnd; x += THREADS) {
         const float d = wta_finish(recL[x], D, P.dmin, P.checkUnique, P.oneMinusRatio);
         rowL[x] = d;
         if (TAPS && P.dispLeftWta) P.dispLeftWta[rowBase + x] = d;
-        if (P.checkLR) {
+    }
+    if (!P.checkLR) return;
+    {   // right-view pixels whose first candidate column x + dmin lies in the segment (+ those without any, at the row's end)
+        const int xEnd = colEnd == W ? W : colEnd - P.dmin;
+        for (int x = max(0, colBegin - P.dmin) + tid; x < xEnd; x += THREADS) {
             const float r = wta_finish(recR[x], D, P.dmin, P.checkUnique, P.oneMinusRatio);
             rowR[x] = r;
             if (TAPS && P.dispRight) P.dispRight[rowBase + x] = r;
         }
     }
-    if (!P.checkLR) return;
-    // ---------------------------------------------------------------------- LR check (:445-470)
-    __syncthreads();
+    // ---------------------------------------------------------------------- LR check (:445-470) of the whole row, by the block
+    // that completes it (a split row: the last of its segments to arrive; nobody waits)
+    if (rowSegs > 1) {
+        __shared__ int lastArrival;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int n = atomicAdd(P.rowDone + y, 1);
+            lastArrival = n == rowSegs - 1;
+            if (n == rowSegs - 1) P.rowDone[y] = 0;
+        }
+        __syncthreads();
+        if (!lastArrival) return;
+        __threadfence();
+    } else {
+        __syncthreads();
+    }
     for (int x = tid; x < W; x += THREADS) {
-        const float d = rowL[x];
+        const float d = __ldcg(rowL + x);
         if (d != sgm_invalid()) {
             const float shifted = __fsub_rn((float)x, d);
             const int xr = __double2int_rz(__dadd_rn((double)shifted, 0.5));
             bool keep = true;
             if (xr < 0 || xr >= W) keep = false;
             else {
-                const float dr = rowR[xr];
+                const float dr = __ldcg(rowR + xr);
                 if (dr != sgm_invalid() && fabsf(__fsub_rn(d, dr)) > P.lrThres) keep = false;
             }
             if (!keep) rowL[x] = sgm_invalid();
         }
     }
+}
+
+template <int CPP, int NP, bool TAPS>
+__global__ void __launch_bounds__(WtaShape<CPP>::kThreads, CPP == 16 ? 1 : 3)
+sgm_reduce_wta_lr(const __grid_constant__ WtaParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
+    __shared__ int item;                           // >= 0: whole row; < 0: piece -1 - item
+    if (P.pieces == 0) {
+        wta_segment<CPP, NP, TAPS>(P, ring, (int)blockIdx.x, 0, P.W, 1);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        const int seen = atomicAdd(P.sched + (sm & (kWtaSchedSms - 1)), 1);
+        int* rowTicket = P.sched + kWtaSchedSms, *pieceTicket = rowTicket + 1;
+        int it;
+        if (seen % (P.rowsPerSm + 1) < P.rowsPerSm) {
+            const int r = atomicAdd(rowTicket, 1);
+            it = r < P.fullRows ? r : -1 - atomicAdd(pieceTicket, 1);
+        } else {
+            const int q = atomicAdd(pieceTicket, 1);
+            it = q < P.pieces ? -1 - q : atomicAdd(rowTicket, 1);
+        }
+        item = it;
+    }
+    __syncthreads();
+    const int it = item;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        int4 sg;
+        if (it >= 0) {
+            if (k) break;
+            sg = make_int4(it, 0, P.W, 1);
+        } else {
+            sg = __ldg(P.segments + 2 * (-1 - it) + k);
+            if (sg.x < 0) break;
+        }
+        if (k) __syncthreads();                   // the ring is re-initialised: everybody has left the previous segment
+        wta_segment<CPP, NP, TAPS>(P, ring, sg.x, sg.y, sg.z, sg.w);
+    }
+    // the last block to finish clears the scheduling state for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) item = atomicAdd(P.sched + kWtaSchedSms + 2, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (item)
+        for (int i = threadIdx.x; i < kWtaSchedInts; i += blockDim.x) P.sched[i] = 0;
 }
 
 }  // namespace sgmb

@@ -342,3 +342,37 @@ def test_random_shapes_and_options_against_oracle(ctx, oracle):
         want = oracle.match(left, right, opts)
         got = run_all_stages(ctx, left, right, opts)
         compare_stages(f"random[{case}] {w}x{h} D={d} dmin={dmin} paths={opts['num_paths']} p1={p1} p2={p2} {tex}", got, want)
+
+
+SPLIT_CASES = [
+    # w, h, planned SM count (0 = the device's), option overrides: shapes whose last partial wave of rows K3 cuts into pieces
+    (700, 40, 16, dict(max_disparity=64)),
+    (500, 37, 10, dict(max_disparity=133, min_disparity=5)),
+    (900, 30, 8, dict(max_disparity=117, min_disparity=17, num_paths=4)),
+    (1300, 20, 3, dict(max_disparity=256)),
+    (450, 50, 0, dict(max_disparity=64)),
+    (333, 29, 6, dict(max_disparity=96, check_lr=False)),
+    (333, 29, 6, dict(max_disparity=96, check_unique=False, lrcheck_thres=0.5)),
+    (640, 11, 4, dict(max_disparity=48, min_disparity=3)),
+]
+
+
+@pytest.mark.parametrize("w,h,sms,kw", SPLIT_CASES)
+def test_k3_row_split_against_oracle(oracle, w, h, sms, kw, monkeypatch):
+    """K3 cuts the rows of the last partial wave into one piece per SM (segments with a halo of D - 1 columns, LR check by the
+    last block to arrive): every stage must stay bit-exact, with the taps on and through the plain hot path."""
+    if sms:
+        monkeypatch.setenv("SGM_B200_DEBUG_WTA_SMS", str(sms))
+    opts = options(**kw)
+    d = opts["max_disparity"] - opts["min_disparity"]
+    left, right, _ = make_pair(w, h, d, seed=0x5eed + w + h, texture="scene")
+    want = oracle.match(left, right, opts)
+    with sgm.Context(0) as c:
+        c.set_pipeline(sgm.PIPE_REFERENCE | sgm.PIPE_TAPS)
+        got = run_all_stages(c, left, right, opts)
+        compare_stages(f"split {w}x{h}x{d} sms={sms}", got, want)
+        c.set_pipeline(sgm.PIPE_REFERENCE)
+        c.configure(w, h, to_sgm_option(opts))
+        for _ in range(3):                                  # the arrival counters reset themselves between frames
+            out = c.match(left, right)
+            assert_same("split:disp_final", out, want["disp_final"])
