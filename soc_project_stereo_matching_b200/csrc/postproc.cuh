@@ -350,10 +350,18 @@ struct AboveFeed {
 };
 
 // 32 steps (kMedianBatch bulk-copy blocks); ringLane: the lane's view of the first of them.  PRED: some lane's column may fall outside the row.
+// Results go to a 32 x 32 shared-memory tile (one conflict-free store per step); a second warp of the block writes the tile out
+// as 32 coalesced row pieces of 128 bytes while the wavefront warp fills the other tile (named barriers, producer /
+// consumer).  A step's 32 results lie in 32 different rows: stored directly they are 32 separate 4-byte transactions, which
+// device memory absorbs but a page-locked HOST buffer does not (SGM_Match at C2 with the caller's buffer written directly:
+// 1.08 ms with scattered stores against 0.65 ms with a device buffer + copy) - and writing the caller's buffer during the
+// filter is what removes the device-to-host copy from the end of SGMB_Match.
+constexpr int kMedianTileStride = 33;
 template <bool HAS_ABOVE, bool PRED, typename Wait, typename Refill>
-__device__ __forceinline__ void median_superblock(MedianLane& st, const float* ringLane, AboveFeed& feed, int colAbove0, float* op, unsigned long long* xp,
+__device__ __forceinline__ void median_superblock(MedianLane& st, const float* ringLane, AboveFeed& feed, int colAbove0, float* tile, unsigned long long* xp,
                                                   int jBase, int Wrow, bool publishes, unsigned tag0, int lane, Wait wait, Refill refill)
 {
+    float* tileLane = tile + lane * kMedianTileStride;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BS = kMedianBlockSteps, NB = kMedianBatch;
 #pragma unroll
@@ -366,10 +374,8 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
             float e4, e5;
             median_fold(ringLane + (k * BS + e) * 5 * 32, 4 * lane, st.a, st.b, st.left, e4, e5);
             const float o = fminf(fmaxf(st.c, e4), e5);
-            if (!PRED || (unsigned)(jBase + off) < (unsigned)Wrow) {
-                op[off] = o;
-                if (publishes) st_relaxed_gpu_u64(xp + off, __float_as_uint(o), tag0 + (unsigned)off);
-            }
+            tileLane[off] = o;
+            if (publishes && (!PRED || (unsigned)(jBase + off) < (unsigned)Wrow)) st_relaxed_gpu_u64(xp + off, __float_as_uint(o), tag0 + (unsigned)off);
             st.left = o;
             float up = __shfl_up_sync(FULL, o, 1);       // out(i-1, j+2): the c of the next step
             if (HAS_ABOVE) {
@@ -383,20 +389,51 @@ __device__ __forceinline__ void median_superblock(MedianLane& st, const float* r
     }
 }
 
+// named barriers of the wavefront block: kMedianBarFull + b: tile b is complete, kMedianBarFree + b: tile b has been written out
+constexpr int kMedianBarFull = 1, kMedianBarFree = 3;
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// The second warp: writes tile after tile to the output rows.  Row r of the group produced columns s0 - 2r .. s0 - 2r + 31
+// in the 32 steps that start at step s0.
+__device__ __forceinline__ void median_flush_tiles(const int g, const float* tiles, float* __restrict__ out, int W, int H)
+{
+    constexpr int Q = kMedianBlockSteps * kMedianBatch;
+    static_assert(Q == 32, "a tile holds the 32 steps of one super-block");
+    const int lane = threadIdx.x & 31;
+    const int nSuper = median_steps_padded(W) / Q;
+    const int rows = min(32, H - 32 * g);
+    float* outRows = out + (size_t)(32 * g) * W;
+    for (int sb = 0; sb < nSuper; ++sb) {
+        const int b = sb & 1;
+        const int s0 = sb * Q - kMedianFrontPad;
+        const float* tile = tiles + b * 32 * kMedianTileStride;
+        bar_sync64(kMedianBarFull + b);
+        float* dst = outRows + s0 + lane;
+        if (s0 >= 62 && s0 + Q <= W) {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) dst[(size_t)r * W - 2 * r] = tile[r * kMedianTileStride + lane];
+        } else {
+            for (int r = 0; r < rows; ++r)
+                if ((unsigned)(s0 - 2 * r + lane) < (unsigned)W) dst[(size_t)r * W - 2 * r] = tile[r * kMedianTileStride + lane];
+        }
+        bar_arrive64(kMedianBarFree + b);
+    }
+}
+
 template <bool HAS_ABOVE>
-__device__ __forceinline__ void median_wavefront_body(const int g, const float* __restrict__ prep, float* __restrict__ out, float* scratchRow,
+__device__ __forceinline__ void median_wavefront_body(const int g, const float* __restrict__ prep, float* __restrict__ out,
                                                       unsigned long long* xchg, int W, int H, unsigned epoch,
-                                                      float (*ring)[kMedianBlockSteps][5][32], unsigned long long* mbar)
+                                                      float (*ring)[kMedianBlockSteps][5][32], unsigned long long* mbar, float* tiles)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int BS = kMedianBlockSteps, NB = kMedianBatch, NR = kMedianRing;
     static_assert(NR % NB == 0 && NR >= NB, "ring must hold whole batches");
     constexpr unsigned kBlockBytes = BS * kMedianStepBytes;
     const int lane = threadIdx.x;
-    const int i = 32 * g + lane;
-    const int Wrow = W;                                                       // rows beyond the image (last group) run like the others and write to a scratch row
+    const int Wrow = W;                                                       // rows beyond the image (last group) run like the others; their results stay in the tile
+    (void)out;
     const bool publishes = (lane == 31) && (32 * (g + 1) < H);                // someone consumes this row
-    float* outRow = (i < H) ? out + (size_t)i * W : scratchRow;
     unsigned long long* myX = xchg + (size_t)g * W;
     const unsigned long long* aboveX = HAS_ABOVE ? xchg + (size_t)(g - 1) * W : nullptr;
     const unsigned tagBase = epoch << 16;
@@ -437,7 +474,6 @@ __device__ __forceinline__ void median_wavefront_body(const int g, const float* 
         const float* ringLane = &ring[slot0][0][0][0];
         const int s0 = sb * NB * BS - kMedianFrontPad;   // first step of the super-block
         const int jBase = s0 - 2 * lane;
-        float* op = outRow + jBase;
         unsigned long long* xp = myX + jBase;
         const unsigned tag0 = tagBase + (unsigned)(jBase + 1);      // == tagBase | (j + 1): j + 1 < 65536
         const unsigned parity = (unsigned)((sb * NB) / NR) & 1u;
@@ -459,8 +495,12 @@ __device__ __forceinline__ void median_wavefront_body(const int g, const float* 
         };
         // all 32 lanes are inside their rows for every step of the super-block <=> s0 >= 62 and s0 + 31 < W (and the row exists)
         const bool interior = s0 >= 62 && s0 + NB * BS <= W;
-        if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, feed, s0 + 2, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
-        else          median_superblock<HAS_ABOVE, true>(st, ringLane, feed, s0 + 2, op, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        const int tb = sb & 1;
+        float* tile = tiles + tb * 32 * kMedianTileStride;
+        if (sb >= 2) bar_sync64(kMedianBarFree + tb);     // the flush warp has written out what this tile held two super-blocks ago
+        if (interior) median_superblock<HAS_ABOVE, false>(st, ringLane, feed, s0 + 2, tile, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        else          median_superblock<HAS_ABOVE, true>(st, ringLane, feed, s0 + 2, tile, xp, jBase, Wrow, publishes, tag0, lane, wait, refill);
+        bar_arrive64(kMedianBarFull + tb);
     }
 #ifdef SGM_MEDIAN_DEBUG
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tEnd));
@@ -470,18 +510,28 @@ __device__ __forceinline__ void median_wavefront_body(const int g, const float* 
 }
 
 // `ticket`: zeroed before every launch (it lives behind the exchange rows and is cleared with them).
-__global__ void __launch_bounds__(32)
-median_wavefront(const float* __restrict__ prep, float* __restrict__ out, float* scratchRow, unsigned long long* xchg, int* ticket,
+__global__ void __launch_bounds__(64)
+median_wavefront(const float* __restrict__ prep, float* __restrict__ out, unsigned long long* xchg, int* ticket,
                  int W, int H, unsigned epoch)
 {
     __shared__ __align__(128) float ring[kMedianRing][kMedianBlockSteps][5][32];
     __shared__ __align__(8) unsigned long long mbar[kMedianRing];
-    int g = 0;
-    if (threadIdx.x == 0) g = atomicAdd(ticket, 1);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g == 0) median_wavefront_body<false>(g, prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
-    else        median_wavefront_body<true>(g, prep, out, scratchRow, xchg, W, H, epoch, ring, mbar);
+    extern __shared__ float tiles[];                       // kMedianTileBytes: two output tiles (beyond the 48 KB of static shared memory)
+    __shared__ int group;
+    if (threadIdx.x == 0) group = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int g = group;
+    if (threadIdx.x >= 32) { median_flush_tiles(g, tiles, out, W, H); return; }
+    if (g == 0) median_wavefront_body<false>(g, prep, out, xchg, W, H, epoch, ring, mbar, tiles);
+    else        median_wavefront_body<true>(g, prep, out, xchg, W, H, epoch, ring, mbar, tiles);
 }
+
+constexpr int kMedianTileBytes = 2 * 32 * kMedianTileStride * (int)sizeof(float);
+// once per device (SGMB_Configure): ring + tiles exceed the default shared-memory limit of a block
+static cudaError_t median_configure() { return cudaFuncSetAttribute(median_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, kMedianTileBytes); }
+
+// argument list of median_wavefront, for the host code that re-points `out` in a recorded graph
+constexpr int kMedianWavefrontArgs = 7, kMedianWavefrontOutArg = 1;
 
 // Bytes of the exchange buffer: one 64-bit (tag, value) word per column and row group, then the ticket counter.
 static size_t median_xchg_bytes(int W, int H) { return ((size_t)((H + 31) / 32) * W + 1) * sizeof(unsigned long long); }
@@ -489,10 +539,9 @@ static size_t median_xchg_bytes(int W, int H) { return ((size_t)((H + 31) / 32) 
 // `epoch` must differ between consecutive launches on the same exchange buffer (never 0: the buffer is
 // zero-initialised), so stale tags of the previous frame are never taken for current ones.
 // in: disparity map before the speckle decision; lab/size: speckle labels (or NULL: no speckle filter).
-// scratchRow: W floats that rows beyond the image write to (never read).
 template <typename Mark>
 static int launch_median3_inplace(const float* in, const int* lab, const int* size, int minArea, float* filteredTap, float* prep,
-                                  float* out, float* scratchRow, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st,
+                                  float* out, unsigned long long* xchg, unsigned* epoch, int W, int H, cudaStream_t st,
                                   Mark mark)
 {
     *epoch = (*epoch % 65535u) + 1u;
@@ -501,7 +550,7 @@ static int launch_median3_inplace(const float* in, const int* lab, const int* si
     median_prepare<<<gp, 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
     mark("median_prepare");
     int* ticket = reinterpret_cast<int*>(xchg + (size_t)groups * W);
-    median_wavefront<<<groups, 32, 0, st>>>(prep, out, scratchRow, xchg, ticket, W, H, *epoch);
+    median_wavefront<<<groups, 64, kMedianTileBytes, st>>>(prep, out, xchg, ticket, W, H, *epoch);
     mark("median_wavefront");
     return kMedianLaunches;
 }

@@ -79,13 +79,17 @@ struct Slot {
     int32_t* labels = nullptr;        // speckle filter scratch [2N]
     unsigned long long* xchg = nullptr;   // median wavefront exchange rows [(H+31)/32][W]
     float* medianPrep = nullptr;      // sorted unfiltered inputs in wavefront order (postproc.cuh K5a)
-    float* medianScratch = nullptr;   // one row that the rows beyond the image of the last row group write to
     uint8_t* framePlanes = nullptr;   // SGMB_MatchFrame: left B,G,R then right B,G,R planes [6][N] (allocated on first use)
     float* depth = nullptr;           // SGMB_MatchFrame with calibration: depth map [N] (allocated on first use)
     unsigned medianEpoch = 0;
     // SGMB_Match / SGMB_MatchBatch always run the frame on the slot's own image buffers, so the whole frame (memsets and
     // kernels) is recorded once into a CUDA graph and replayed by every later call until the configuration changes
     cudaGraphExec_t frameExec = nullptr;
+    // the recorded graph itself (its node handles are needed to re-point the last kernel at the caller's buffer), the median
+    // wavefront's node in it, and the output pointer the executable graph currently holds
+    cudaGraph_t frameGraph = nullptr;
+    cudaGraphNode_t medianNode = nullptr;
+    float* frameOut = nullptr;
     bool busy = false;
     // Pageable caller memory (malloc / static arrays, e.g. the reference demo main.c:25-26,81) is staged through page-locked
     // buffers owned by the slot (allocated on first use): stageIn = both images in the layout of img[], stageOut = result.
@@ -146,6 +150,8 @@ static int ensure_device(SGMB_Context* c)
 static void drop_frame_graph(Slot& s)
 {
     if (s.frameExec) { cudaGraphExecDestroy(s.frameExec); s.frameExec = nullptr; }
+    if (s.frameGraph) { cudaGraphDestroy(s.frameGraph); s.frameGraph = nullptr; }
+    s.medianNode = nullptr; s.frameOut = nullptr;
 }
 
 static void free_slot_buffers(Slot& s)
@@ -158,7 +164,6 @@ static void free_slot_buffers(Slot& s)
     cudaFree(s.side); cudaFree(s.S); cudaFree(s.dispLeftWta); cudaFree(s.dispRight); cudaFree(s.dispLR);
     cudaFree(s.framePlanes); cudaFree(s.depth); s.framePlanes = nullptr; s.depth = nullptr;
     cudaFree(s.pixL); s.pixL = nullptr;
-    cudaFree(s.medianScratch); s.medianScratch = nullptr;
     cudaFree(s.dispSpeckle); cudaFree(s.dispFinal); cudaFree(s.labels); cudaFree(s.xchg); cudaFree(s.medianPrep); cudaFree(s.rightRow); cudaFree(s.wtaRecords); cudaFree(s.wtaRowDone); cudaFree(s.wtaSched);
     s.img[0] = s.img[1] = nullptr; s.censusL = s.censusR4 = nullptr; s.planes = nullptr; s.side = nullptr; s.S = nullptr;
     s.dispLeftWta = s.dispRight = s.dispLR = s.dispSpeckle = s.dispFinal = nullptr; s.labels = nullptr; s.xchg = nullptr; s.medianPrep = nullptr; s.rightRow = nullptr; s.wtaRecords = nullptr; s.wtaRowDone = nullptr; s.wtaSched = nullptr;
@@ -379,6 +384,8 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         else                  rc = wta_prepare<16>(c);
         if (rc == SGMB_OK) rc = wta_plan(c);
         if (rc) return rc;
+        CU(median_configure());
+        if (rc) return rc;
     }
 
     // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
@@ -476,7 +483,6 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         CU(cudaMalloc(&s.xchg, xbytes));
         CU(cudaMemset(s.xchg, 0, xbytes));
         // slots of idle (row, step) pairs are never written and must hold ordinary floats
-        CU(cudaMalloc(&s.medianScratch, ((size_t)W + 64) * sizeof(float)));
         CU(cudaMalloc(&s.medianPrep, median_prep_floats(W, H) * sizeof(float)));
         CU(cudaMemset(s.medianPrep, 0, median_prep_floats(W, H) * sizeof(float)));
         s.medianEpoch = 0;
@@ -653,36 +659,81 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
     }
     if (doMedian) {
         // the component sizes are applied while the median's inputs are gathered; dispSpeckle is a tap
+        // without taps nobody reads dispFinal: the wavefront writes the caller's buffer itself (it only ever writes `out`)
+        float* fin = (dOut && !taps) ? dOut : s.dispFinal;
         nk += launch_median3_inplace(cur, lab, lab ? lab + c->N : nullptr, c->opt.min_speckle_area, (taps && lab) ? s.dispSpeckle : nullptr,
-                                     s.medianPrep, s.dispFinal, s.medianScratch, s.xchg, &s.medianEpoch, W, H, s.stream, mark);
-        cur = s.dispFinal;
+                                     s.medianPrep, fin, s.xchg, &s.medianEpoch, W, H, s.stream, mark);
+        cur = fin;
     }
-    if (dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
+    if (dOut && cur != dOut) CU(cudaMemcpyAsync(dOut, cur, c->N * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
     CU(cudaGetLastError());
     if (launches) *launches = nk;
     return SGMB_OK;
 }
 
-// The frame on the slot's own image buffers: recorded into a graph on first use, replayed afterwards.
-static int launch_slot_frame(SGMB_Context* c, Slot& s)
+// Device-side address of caller memory the last kernel of the frame may write directly: page-locked host memory
+// (cudaHostAlloc / cudaHostRegister / SGMB_HostAlloc) when the frame ends with the median and no taps are kept.
+static float* direct_output(SGMB_Context* c, float* out)
+{
+    if (!out || !(c->pipeline & SGMB_PIPE_MEDIAN) || (c->pipeline & SGMB_PIPE_TAPS)) return nullptr;
+    static const bool off = getenv("SGM_B200_NO_DIRECT_OUT") != nullptr;
+    if (off) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, out) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? static_cast<float*>(a.devicePointer) : nullptr;
+}
+
+// The frame on the slot's own image buffers: recorded into a graph on first use, replayed afterwards.  `direct` (from
+// direct_output(), or NULL): the median wavefront writes there instead of dispFinal - the node's `out` argument of the
+// executable graph is re-pointed when it differs from the previous call's - and *wroteDirect tells the caller to skip its copy.
+static int launch_slot_frame(SGMB_Context* c, Slot& s, float* direct = nullptr, bool* wroteDirect = nullptr)
 {
     static const bool noGraph = getenv("SGM_B200_NO_GRAPH") != nullptr;
-    if (noGraph) return enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr);
+    if (wroteDirect) *wroteDirect = false;
+    if (noGraph) {
+        if (wroteDirect) *wroteDirect = direct != nullptr;
+        return enqueue_frame(c, s, s.img[0], s.img[1], direct, false, nullptr);
+    }
     if (!s.frameExec) {
-        cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         c->capturing = true;
         int rc = enqueue_frame(c, s, s.img[0], s.img[1], nullptr, false, nullptr);
         c->capturing = false;
-        const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        const cudaError_t e = cudaStreamEndCapture(s.stream, &s.frameGraph);
         if (rc == SGMB_OK && e != cudaSuccess) rc = fail(SGMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
         if (rc == SGMB_OK) {
-            const cudaError_t e2 = cudaGraphInstantiate(&s.frameExec, graph, 0);
+            const cudaError_t e2 = cudaGraphInstantiate(&s.frameExec, s.frameGraph, 0);
             if (e2 != cudaSuccess) { s.frameExec = nullptr; rc = fail(SGMB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
         }
-        if (graph) cudaGraphDestroy(graph);
-        if (rc) return rc;
+        if (rc == SGMB_OK) {
+            size_t n = 0;
+            CU(cudaGraphGetNodes(s.frameGraph, nullptr, &n));
+            std::vector<cudaGraphNode_t> nodes(n);
+            CU(cudaGraphGetNodes(s.frameGraph, nodes.data(), &n));
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType t;
+                CU(cudaGraphNodeGetType(nd, &t));
+                if (t != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp{};
+                CU(cudaGraphKernelNodeGetParams(nd, &kp));
+                if (kp.func == reinterpret_cast<void*>(&median_wavefront)) s.medianNode = nd;
+            }
+            s.frameOut = s.dispFinal;
+        }
+        if (rc) { drop_frame_graph(s); return rc; }
     }
+    float* want = (direct && s.medianNode) ? direct : s.dispFinal;
+    if (s.medianNode && want != s.frameOut) {
+        cudaKernelNodeParams kp{};
+        CU(cudaGraphKernelNodeGetParams(s.medianNode, &kp));
+        void* args[kMedianWavefrontArgs];
+        for (int i = 0; i < kMedianWavefrontArgs; ++i) args[i] = kp.kernelParams[i];
+        args[kMedianWavefrontOutArg] = &want;
+        kp.kernelParams = args;
+        CU(cudaGraphExecKernelNodeSetParams(s.frameExec, s.medianNode, &kp));
+        s.frameOut = want;
+    }
+    if (wroteDirect) *wroteDirect = want == direct && direct != nullptr;
     CU(cudaGraphLaunch(s.frameExec, s.stream));
     return SGMB_OK;
 }
@@ -762,8 +813,9 @@ extern "C" int SGMB_Match(SGMB_Context* c, const uint8_t* L, const uint8_t* R, f
     const int rc = [&]() -> int {
         CU(cudaEventRecord(s.evStart, s.stream));
         if (int rc = copy_in(c, s, L, R, false)) return rc;
-        if (int rc = launch_slot_frame(c, s)) return rc;
-        if (out) if (int rc = copy_out(c, s, out, false)) return rc;
+        bool wrote = false;
+        if (int rc = launch_slot_frame(c, s, direct_output(c, out), &wrote)) return rc;
+        if (out && !wrote) if (int rc = copy_out(c, s, out, false)) return rc;
         CU(cudaEventRecord(s.evStop, s.stream));
         CU(cudaStreamSynchronize(s.stream));
         CU(cudaEventElapsedTime(&c->lastMs, s.evStart, s.evStop));
@@ -818,8 +870,9 @@ static int run_batch(SGMB_Context* c, const uint8_t* const* Ls, const uint8_t* c
                 if (int rc = enqueue_frame(c, s, Ls[k], Rs[k], outs[k], false, nullptr)) return rc;
             } else {
                 if (int rc = copy_in(c, s, Ls[k], Rs[k], true)) return rc;
-                if (int rc = launch_slot_frame(c, s)) return rc;
-                if (int rc = copy_out(c, s, outs[k], true)) return rc;
+                bool wrote = false;
+                if (int rc = launch_slot_frame(c, s, direct_output(c, outs[k]), &wrote)) return rc;
+                if (!wrote) if (int rc = copy_out(c, s, outs[k], true)) return rc;
             }
         }
         for (int j = 1; j < c->nslots; ++j) {
