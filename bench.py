@@ -300,6 +300,21 @@ def main() -> int:
     barrier()
     e2e_pg_s = max_over_ranks(time.perf_counter() - t0)
     assert np.array_equal(pg_o.view(np.uint32), np_o.view(np.uint32)), "pageable and page-locked calls disagree"
+    # ... and the same malloc'd arrays page-locked in place with SGMB_HostRegister (what INTEGRATION.md adds to main.c)
+    for a in (pg_l, pg_r, pg_o):
+        assert sgm.lib.SGMB_HostRegister(a.ctypes.data, a.nbytes) == 0, sgm.last_error()
+    pg_o[:] = -1.0
+    for _ in range(args.warmup):
+        assert sgm.SGM_Match(pg_l, pg_r, pg_o)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sgm.SGM_Match(pg_l, pg_r, pg_o)
+    barrier()
+    e2e_reg_s = max_over_ranks(time.perf_counter() - t0)
+    assert np.array_equal(pg_o.view(np.uint32), np_o.view(np.uint32)), "registered and page-locked calls disagree"
+    for a in (pg_l, pg_r, pg_o):
+        assert sgm.lib.SGMB_HostUnregister(a.ctypes.data) == 0, sgm.last_error()
     # same call sequence restricted to the hot path (no speckle filter / median), host buffers
     ctx.set_pipeline(sgm.PIPE_HOTPATH)
     for _ in range(args.warmup):
@@ -453,10 +468,14 @@ def main() -> int:
             "e2e": {"value": e2e_value, "unit": "MDE/s", "h2d_bytes_per_step": 2 * W * H, "d2h_bytes_per_step": 4 * W * H,
                     "ms_per_step": e2e_s / args.steps * 1e3, "span": "SGM_Match: hot path + speckle filter + in-place median",
                     "host_buffers": "page-locked",
+                    "d2h": "the last kernel (median wavefront) writes the page-locked output buffer itself, 128-byte row pieces over PCIe; "
+                           "no copy-engine pass at the end of the call (SGM_B200_NO_DIRECT_OUT=1 restores the copy)",
                     "hotpath_only": {"value": world * args.steps * de_per_frame / e2e_hot_s / 1e6, "ms_per_step": e2e_hot_s / args.steps * 1e3}},
             "e2e_pageable": {"value": world * args.steps * de_per_frame / e2e_pg_s / 1e6, "unit": "MDE/s", "ms_per_step": e2e_pg_s / args.steps * 1e3,
                              "host_buffers": "pageable (malloc'd numpy arrays, as main.c:25-26,81 passes)", "h2d_bytes_per_step": 2 * W * H,
                              "d2h_bytes_per_step": 4 * W * H},
+            "e2e_registered": {"value": world * args.steps * de_per_frame / e2e_reg_s / 1e6, "unit": "MDE/s", "ms_per_step": e2e_reg_s / args.steps * 1e3,
+                               "host_buffers": "the same malloc'd arrays after SGMB_HostRegister"},
             "gpu_launches": gpu_launches,
             "gpu_launches_note": f"{launches_per_frame} kernels per hot-path frame in the `value` region (x {max(1, args.replays)} replays in total); SGM_Match launches {gctx_launches} per frame",
             "batched": batched,

@@ -103,6 +103,8 @@ def _load() -> C.CDLL:
         "SGMB_CompareDepthDevice": (i32, [vp, vp, vp, C.c_size_t, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
         "SGMB_HostAlloc": (i32, [C.POINTER(vp), C.c_size_t]),
         "SGMB_HostFree": (None, [vp]),
+        "SGMB_HostRegister": (i32, [vp, C.c_size_t]),
+        "SGMB_HostUnregister": (i32, [vp]),
         "SGMB_KernelLaunchesPerFrame": (i32, [vp]),
         "SGMB_ModelBytesPerFrame": (C.c_double, [vp]),
         "SGMB_PlanBytesPerFrame": (C.c_double, [vp]),

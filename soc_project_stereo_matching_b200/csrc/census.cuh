@@ -42,25 +42,34 @@ struct CensusParams {
 
 constexpr int kCensusTileW = 64;
 constexpr int kCensusTileH = 8;
+constexpr int kCensusPerThread = 4;      // horizontally adjacent outputs per thread
+constexpr int kCensusThreads = kCensusTileW * kCensusTileH / kCensusPerThread;
 
 template <int CW, int CH, typename DT, bool PLANAR>
-__global__ void __launch_bounds__(kCensusTileW * kCensusTileH / 2)
+__global__ void __launch_bounds__(kCensusThreads)
 sgm_census(CensusParams P)
 {
-    // tile of 64 x 8 outputs, (64 + CW - 1) x (8 + CH - 1) inputs; every thread produces two horizontally adjacent outputs
-    constexpr int RX = CW / 2, RY = CH / 2, K = 16 / (int)sizeof(DT);
-    constexpr int TW = kCensusTileW + CW - 1, TH = kCensusTileH + CH - 1;
-    __shared__ uint8_t tile[TH][TW + 4];
+    // tile of 64 x 8 outputs, (64 + CW - 1) x (8 + CH - 1) inputs; every thread produces four horizontally adjacent outputs:
+    // their windows span 4 + CW - 1 columns, fetched as 32-bit words (2 per row for 5x5, 3 for 9x7: 10 loads instead of the
+    // 100 byte loads of four separate windows), the bytes picked with PRMT at compile-time positions
+    constexpr int RX = CW / 2, RY = CH / 2, K = 16 / (int)sizeof(DT), PX = kCensusPerThread;
+    constexpr int TW = kCensusTileW + CW - 1, TH = kCensusTileH + CH - 1, TP = (TW + 3 + 3) & ~3, NWORD = (PX + CW - 1 + 3) / 4;
+    __shared__ __align__(16) uint8_t tile[TH][TP];
     const int which = blockIdx.z;
     const uint8_t* __restrict__ img = which ? P.img[1] : P.img[0];
     const int W = P.W, H = P.H;
     const int x0 = blockIdx.x * kCensusTileW, y0 = blockIdx.y * kCensusTileH;
 
-    for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
+    // all loads of the staging pass are issued before the first shared-memory store (one round trip to memory, not ITER)
+    constexpr int ITER = (TH * TW + kCensusThreads - 1) / kCensusThreads;
+    uint8_t staged[ITER];
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int i = threadIdx.x + k * kCensusThreads;
         const int ty = i / TW, tx = i % TW;
         const int y = y0 + ty - RY, x = x0 + tx - RX;
         uint8_t v = 0;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
+        if (i < TH * TW && y >= 0 && y < H && x >= 0 && x < W) {
             const size_t p = (size_t)y * W + x;
             if (PLANAR) {
                 const size_t N = (size_t)W * H;
@@ -71,31 +80,55 @@ sgm_census(CensusParams P)
                 v = __ldg(img + p);
             }
         }
-        tile[ty][tx] = v;
+        staged[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int i = threadIdx.x + k * kCensusThreads;
+        if (i < TH * TW) tile[i / TW][i % TW] = staged[k];
     }
     __syncthreads();
 
-    const int ty = threadIdx.x / (kCensusTileW / 2);
-    const int tx = (threadIdx.x % (kCensusTileW / 2)) * 2;
+    const int ty = threadIdx.x / (kCensusTileW / PX);
+    const int tx = (threadIdx.x % (kCensusTileW / PX)) * PX;
     const int y = y0 + ty;
     if (y >= H) return;
+    uint32_t b[CH][PX + CW - 1];                              // b[r][c] = tile[ty + r][tx + c]: every byte is extracted once for all four windows
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
+    for (int r = 0; r < CH; ++r)
+#pragma unroll
+        for (int k = 0; k < NWORD; ++k) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[ty + r][tx + 4 * k]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * k + j < PX + CW - 1) b[r][4 * k + j] = __byte_perm(w, 0u, 0x4440u | (uint32_t)j);
+        }
+    auto px = [&](int r, int c) -> uint32_t { return b[r][c]; };
+#pragma unroll
+    for (int o = 0; o < PX; ++o) {
         const int x = x0 + tx + o;
         if (x >= W) break;
         DT bits = 0;
+        const uint32_t centre = px(RY, o + RX);
         if (y >= RY && y < H - RY && x >= RX && x < W - RX && W > CW && H > CH) {
-            const uint32_t centre = tile[ty + RY][tx + o + RX];
+            // "neighbour < centre" is the sign of (neighbour - centre); a funnel shift moves it into the descriptor: two
+            // instructions per comparison.  64-bit descriptors are built as two 32-bit words (the last 32 comparisons: low word).
+            uint32_t acc[2] = {0u, 0u};
 #pragma unroll
             for (int r = 0; r < CH; ++r)
 #pragma unroll
-                for (int c = 0; c < CW; ++c)
-                    bits = (bits << 1) | (DT)(tile[ty + r][tx + o + c] < centre);
+                for (int c = 0; c < CW; ++c) {
+                    constexpr int total = CW * CH;
+                    const int word = (sizeof(DT) == 8 && r * CW + c < total - 32) ? 0 : 1;
+                    acc[word] = __funnelshift_l(px(r, o + c) - centre, acc[word], 1);
+                }
+            bits = (DT)acc[1];
+            if (sizeof(DT) == 8) bits |= (DT)((unsigned long long)acc[0] << 32);
         }
         const size_t p = (size_t)y * W + x;
         if (which == 0) {
             static_cast<DT*>(P.left)[p] = bits;
-            const uint32_t grey = tile[ty + RY][tx + o + RX];
+            const uint32_t grey = centre;
             if (sizeof(DT) == 4) static_cast<uint2*>(P.pixL)[p] = make_uint2((uint32_t)bits, grey);
             else static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
         } else {

@@ -560,7 +560,7 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         p.pixL = s.pixL;
         p.wR = (c->greyFormula == SGMB_GREY_STB) ? 77u : 76u; p.wG = 150u; p.wB = 29u;
         dim3 grid((W + kCensusTileW - 1) / kCensusTileW, (H + kCensusTileH - 1) / kCensusTileH, 2);
-        const int threads = kCensusTileW * kCensusTileH / 2;
+        const int threads = kCensusThreads;
         if (c->descBytes == 4) {
             if (planar) sgm_census<5, 5, uint32_t, true><<<grid, threads, 0, s.stream>>>(p);
             else        sgm_census<5, 5, uint32_t, false><<<grid, threads, 0, s.stream>>>(p);
@@ -1237,6 +1237,22 @@ extern "C" int SGMB_HostAlloc(void** out, size_t bytes)
 }
 
 extern "C" void SGMB_HostFree(void* p) { if (p) cudaFreeHost(p); }
+
+// Page-lock memory the caller already owns (malloc, static arrays - what main.c:25-26,81 passes), so that SGM_Match reads and
+// writes it without the driver's staging copies.  The range must be unregistered before it is freed.
+extern "C" int SGMB_HostRegister(void* p, size_t bytes)
+{
+    if (!p || !bytes) return fail(SGMB_E_ARG, "SGMB_HostRegister: NULL pointer or zero size");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return SGMB_OK;
+}
+
+extern "C" int SGMB_HostUnregister(void* p)
+{
+    if (!p) return fail(SGMB_E_ARG, "SGMB_HostUnregister: NULL pointer");
+    CU(cudaHostUnregister(p));
+    return SGMB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ introspection
 extern "C" int SGMB_KernelLaunchesPerFrame(SGMB_Context* c)

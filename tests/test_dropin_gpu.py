@@ -89,6 +89,46 @@ def test_pinned_and_pageable_host_buffers_give_the_same_result(oracle):
                 sgm.lib.SGMB_HostFree(p)
 
 
+def test_registered_caller_memory_and_direct_output(oracle):
+    """Caller-owned arrays page-locked with SGMB_HostRegister: the last kernel writes the output buffer directly (no copy at
+    the end of the call).  The buffer is pre-filled with garbage, several calls alternate between two output buffers and a
+    pageable one (the recorded graph's output argument is re-pointed each time), and a batch writes five registered outputs."""
+    w, h, d = 333, 75, 96
+    opts = options(max_disparity=d)
+    pairs = [make_pair(w, h, d, seed=500 + k, texture="scene")[:2] for k in range(2)]
+    wants = [oracle.match(l, r, opts, stages=False)["disp_final"] for l, r in pairs]
+    outs = [np.full((h, w), -7.0, np.float32) for _ in range(2)]
+    batch_out = np.full((5, h, w), -3.0, np.float32)
+    pageable = np.full((h, w), -5.0, np.float32)
+    reg = [a for pr in pairs for a in pr] + outs + [batch_out]
+    for a in reg:
+        assert sgm.lib.SGMB_HostRegister(a.ctypes.data, a.nbytes) == 0, sgm.last_error()
+    try:
+        with sgm.Context(0, slots=2) as c:
+            c.configure(w, h, to_sgm_option(opts))
+            for rep in range(6):
+                k = rep % 2
+                (l, r), dst = pairs[k], (pageable if rep == 3 else outs[(rep // 2) % 2])
+                dst[:] = -9.0
+                c.match_ptr(l.ctypes.data, r.ctypes.data, dst.ctypes.data)
+                assert_same(f"registered rep {rep}", dst, wants[k])
+            c.match_batch_ptrs([pairs[k % 2][0].ctypes.data for k in range(5)], [pairs[k % 2][1].ctypes.data for k in range(5)],
+                               [batch_out[k].ctypes.data for k in range(5)])
+            for k in range(5):
+                assert_same(f"registered batch[{k}]", batch_out[k], wants[k % 2])
+            # with the taps on the result also has to stay readable as a stage: the copy path is used
+            c.set_pipeline(sgm.PIPE_REFERENCE | sgm.PIPE_TAPS)
+            c.configure(w, h, to_sgm_option(opts))
+            outs[0][:] = -9.0
+            c.match_ptr(pairs[0][0].ctypes.data, pairs[0][1].ctypes.data, outs[0].ctypes.data)
+            assert_same("registered, taps on", outs[0], wants[0])
+            assert_same("stage disp_final", c.stage("disp_final"), wants[0])
+    finally:
+        for a in reg:
+            assert sgm.lib.SGMB_HostUnregister(a.ctypes.data) == 0, sgm.last_error()
+    assert sgm.lib.SGMB_HostRegister(None, 16) != 0 and sgm.lib.SGMB_HostUnregister(None) != 0
+
+
 def test_two_live_contexts_with_different_disparity_ranges(oracle):
     """The opt-in shared-memory size of the WTA kernel is a per-function attribute shared by all contexts of the process:
     configuring a second context with a smaller range must not break the first one (D=128 then D=112; D=256 then D=200)."""
