@@ -278,40 +278,37 @@ def main() -> int:
     sgm.lib.SGMB_SetGlobalDevice(local_rank)
     assert sgm.SGM_Initialize(W, H, opt), sgm.last_error()
     np_l, np_r, np_o = h_left.numpy(), h_right.numpy(), h_out.numpy()
-    for _ in range(args.warmup):
-        assert sgm.SGM_Match(np_l, np_r, np_o)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ok = sgm.SGM_Match(np_l, np_r, np_o)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    assert ok, sgm.last_error()
+    # the timed call is the C symbol itself (bool SGM_Match(const uint8_t*, const uint8_t*, float*)) on resolved pointers: the
+    # Python wrapper's per-call argument checks (~15 us) are not part of the library
+    import ctypes as C
+    c_match = sgm.lib.SGM_Match
+
+    def timed_calls(a_l, a_r, a_o):
+        pl, pr, po = (C.c_void_p(a.ctypes.data) for a in (a_l, a_r, a_o))
+        for _ in range(args.warmup):
+            assert c_match(pl, pr, po), sgm.last_error()
+        barrier()
+        t_begin = time.perf_counter()
+        for _ in range(args.steps):
+            good = c_match(pl, pr, po)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t_begin)
+        assert good, sgm.last_error()
+        return dt
+
+    assert sgm.SGM_Match(np_l, np_r, np_o)                  # once through the checked wrapper
+    e2e_s = timed_calls(np_l, np_r, np_o)
     e2e_value = world * args.steps * de_per_frame / e2e_s / 1e6
-    gctx_launches = 3 + 3 + 2
+    gctx_launches = sgm.lib.SGMB_KernelLaunchesPerFrame(sgm.lib.SGMB_GlobalContext())
     # the same call with pageable (malloc'd) buffers: what the reference demo passes (main.c:25-26,81)
     pg_l, pg_r, pg_o = left.copy(), right.copy(), np.zeros((H, W), np.float32)
-    for _ in range(args.warmup):
-        assert sgm.SGM_Match(pg_l, pg_r, pg_o)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sgm.SGM_Match(pg_l, pg_r, pg_o)
-    barrier()
-    e2e_pg_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_pg_s = timed_calls(pg_l, pg_r, pg_o)
     assert np.array_equal(pg_o.view(np.uint32), np_o.view(np.uint32)), "pageable and page-locked calls disagree"
     # ... and the same malloc'd arrays page-locked in place with SGMB_HostRegister (what INTEGRATION.md adds to main.c)
     for a in (pg_l, pg_r, pg_o):
         assert sgm.lib.SGMB_HostRegister(a.ctypes.data, a.nbytes) == 0, sgm.last_error()
     pg_o[:] = -1.0
-    for _ in range(args.warmup):
-        assert sgm.SGM_Match(pg_l, pg_r, pg_o)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sgm.SGM_Match(pg_l, pg_r, pg_o)
-    barrier()
-    e2e_reg_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_reg_s = timed_calls(pg_l, pg_r, pg_o)
     assert np.array_equal(pg_o.view(np.uint32), np_o.view(np.uint32)), "registered and page-locked calls disagree"
     for a in (pg_l, pg_r, pg_o):
         assert sgm.lib.SGMB_HostUnregister(a.ctypes.data) == 0, sgm.last_error()
