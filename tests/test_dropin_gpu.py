@@ -116,6 +116,13 @@ def test_registered_caller_memory_and_direct_output(oracle):
                                [batch_out[k].ctypes.data for k in range(5)])
             for k in range(5):
                 assert_same(f"registered batch[{k}]", batch_out[k], wants[k % 2])
+            with sgm.Context(0, slots=1) as one:             # a single-slot context writes batch results directly as well
+                one.configure(w, h, to_sgm_option(opts))
+                batch_out[:] = -3.0
+                one.match_batch_ptrs([pairs[k % 2][0].ctypes.data for k in range(5)], [pairs[k % 2][1].ctypes.data for k in range(5)],
+                                     [batch_out[k].ctypes.data for k in range(5)])
+                for k in range(5):
+                    assert_same(f"registered batch, one slot [{k}]", batch_out[k], wants[k % 2])
             # with the taps on the result also has to stay readable as a stage: the copy path is used
             c.set_pipeline(sgm.PIPE_REFERENCE | sgm.PIPE_TAPS)
             c.configure(w, h, to_sgm_option(opts))
