@@ -301,13 +301,14 @@ __device__ __forceinline__ void median_fold(const float* A, int lane4, float a, 
     e5 = fminf(fminf(A5, fmaxf(A4, B1)), fminf(fmaxf(A3, B2), fmaxf(A2, B3)));
 }
 
-// Values of the last row of the group above (row 32g - 1), eight columns at a time.  The producer publishes every column as
+// Values of the last row of the group above (row 32g - 1), kMedianFeed columns at a time.  The producer publishes every column as
 // it is computed; the consumer takes them in pieces of kMedianFeed columns - lanes 0 .. kMedianFeed-1 hold the current
 // piece, the next piece is requested when the current one is taken over and verified (tag) when its turn comes.  The
 // piece size sets how far a group must trail its predecessor: 62 steps by construction (lane 31 of the group above is 62
 // steps behind its lane 0) + one piece + one piece of prefetch distance + the store-to-poll latency.  With 32-column
 // pieces fetched 32 steps ahead (round 1) a group trailed by ~170 steps = 7.6 us, and the whole filter was groups x that.
-constexpr int kMedianFeed = 8;
+// Piece size, measured at C2 with the tile-staged output (median_wavefront, us): 4: 170, 8: 129, 16: 126, 32: 137; C3: 8: 493, 16: 452.
+constexpr int kMedianFeed = 16;
 struct AboveFeed {
     const unsigned long long* aboveX;
     int W, lane;
