@@ -431,7 +431,7 @@ def main() -> int:
             issue_frac = ncu_facts["warp_instructions"] / (148 * 4 * sm_hz * agg_avg_ms * 1e-3)
         # bytes every kernel of the frame has to move in this implementation (planes written once by K2, read once by K3)
         n_px, dp = W * H, (D + 15) // 16 * 16
-        plan_bytes = {"sgm_census": n_px * (2 + 4 + 8 + 16), "sgm_aggregate_paths": n_px * (PATHS * dp + 12 + 16),
+        plan_bytes = {"sgm_census": n_px * (2 + 4 + 8 + 32), "sgm_aggregate_paths": n_px * (PATHS * dp + 12 + 32),
                       "sgm_reduce_wta_lr": n_px * (PATHS * dp + 2 * 16 * 2 + 8), "speckle_init": n_px * 12, "speckle_merge": n_px * 8,
                       "speckle_count": n_px * 8, "median_prepare": n_px * (4 + 8 + 20), "median_wavefront": n_px * (20 + 4)}
         kernels = [{"name": k, "ms": ms, "plan_bytes": plan_bytes.get(k), "frac_hbm": (plan_bytes[k] / (ms * 1e-3) / 1e9 / peak) if k in plan_bytes and ms > 0 else None}

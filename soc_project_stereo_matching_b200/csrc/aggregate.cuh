@@ -57,7 +57,7 @@ struct AggParams {
     const void* pixL;           // {left descriptor, grey value} per pixel - uint2 for 32-bit descriptors, uint4 {lo, hi, grey, 0} for
                                 // 64-bit ones: what a column visit needs besides its right-census window, fetched with ONE vector
                                 // load (see load_step)
-    const void* censusR4;       // DT [16 / sizeof(DT)][copyStride], see census.cuh
+    const void* censusR4;       // DT [32 / sizeof(DT)][copyStride], see census.cuh
     uint32_t copyStride;        // elements per copy (< 2^31)
     int padF;
     uint8_t* planes;            // [8][planeStride]
@@ -72,7 +72,10 @@ struct AggParams {
     uint32_t p2x2[256];         // min(256, max(P1, P2_init/(delta+1))) in both fields, indexed by |g - gPrev|
 };
 
-constexpr int kAggWarpsPerBlock = 4;
+#ifndef SGM_AGG_WPB
+#define SGM_AGG_WPB 4
+#endif
+constexpr int kAggWarpsPerBlock = SGM_AGG_WPB;
 
 // ------------------------------------------------------------------------------------------------ shared pieces
 template <int NR, typename DT>
@@ -88,8 +91,8 @@ template <int NR, typename DT>
 __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int sub, StepInput<NR, DT>& in)
 {
     constexpr int DPL = 2 * NR;
-    constexpr int PER16 = 16 / (int)sizeof(DT);           // descriptors per 128-bit load
-    constexpr int VEC = DPL < PER16 ? DPL : PER16;        // alignment unit of the window, in descriptors
+    constexpr int PER32 = 32 / (int)sizeof(DT);           // descriptors per 256-bit load
+    constexpr int VEC = DPL < PER32 ? DPL : PER32;        // alignment unit of the window, in descriptors
     if constexpr (sizeof(DT) == 4) {
         // One 64-bit load instead of two scalar ones.  With scalar loads ptxas let the load overwrite its own address
         // register and parked the value with a register move a few instructions later - a full L2 latency on the
@@ -108,24 +111,37 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
         const uint4 px = __ldg(static_cast<const uint4*>(P.pixL) + pos);
         in.cl = ((desc64_t)px.y << 32) | px.x; in.g = px.z;
     }
+    // The window of a lane is DPL consecutive descriptors, and the lanes of a path sit DPL descriptors apart, so ONE load
+    // instruction of a warp touches (lanes) pieces that are DPL * sizeof(DT) bytes apart: the L1 data pipe needs a pass
+    // ("wavefront") per 128-byte line touched, not per byte delivered.  With 128-bit loads a visit of the 8 x 16 layout cost
+    // 4 instructions x ~17 lines; ncu (round 2, r2_y): l1tex data-pipe wavefronts 78 % of peak, 77 per visit, and the SMs that
+    // hold only column-like warps finished last, in proportion to their wavefront count.  256-bit loads (LDG.E.256, new on
+    // sm_100; the address must be 32-byte aligned, hence 32 / sizeof(DT) shifted copies of the right census instead of
+    // 16 / sizeof(DT)) halve the instructions while each still touches the same lines: ~36 wavefronts per visit.
     const uint32_t y0 = pos - (uint32_t)(P.dmin + DPL * sub + (DPL - 1)) + (uint32_t)P.padF;   // >= 0 by the front padding
     const uint32_t al = (y0 + (VEC - 1)) & ~(uint32_t)(VEC - 1);
     const DT* src = static_cast<const DT*>(P.censusR4) + ((al - y0) * P.copyStride + al);
     if constexpr (sizeof(DT) == 4 && VEC == 2) {
         const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
         in.v[0] = t.x; in.v[1] = t.y;
+    } else if constexpr (sizeof(DT) == 4 && VEC == 4) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(src));
+        in.v[0] = t.x; in.v[1] = t.y; in.v[2] = t.z; in.v[3] = t.w;
     } else if constexpr (sizeof(DT) == 4) {
 #pragma unroll
-        for (int j = 0; j < DPL / 4; ++j) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + j);
-            in.v[4 * j + 0] = t.x; in.v[4 * j + 1] = t.y; in.v[4 * j + 2] = t.z; in.v[4 * j + 3] = t.w;
-        }
+        for (int j = 0; j < DPL / 8; ++j)
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(in.v[8 * j]), "=r"(in.v[8 * j + 1]), "=r"(in.v[8 * j + 2]), "=r"(in.v[8 * j + 3]),
+                           "=r"(in.v[8 * j + 4]), "=r"(in.v[8 * j + 5]), "=r"(in.v[8 * j + 6]), "=r"(in.v[8 * j + 7])
+                         : "l"(src + 8 * j));
+    } else if constexpr (VEC == 2) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(src));
+        in.v[0] = ((desc64_t)t.y << 32) | t.x; in.v[1] = ((desc64_t)t.w << 32) | t.z;
     } else {
 #pragma unroll
-        for (int j = 0; j < DPL / 2; ++j) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + j);
-            in.v[2 * j + 0] = ((desc64_t)t.y << 32) | t.x; in.v[2 * j + 1] = ((desc64_t)t.w << 32) | t.z;
-        }
+        for (int j = 0; j < DPL / 4; ++j)
+            asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(in.v[4 * j]), "=l"(in.v[4 * j + 1]), "=l"(in.v[4 * j + 2]), "=l"(in.v[4 * j + 3]) : "l"(src + 4 * j));
     }
 }
 
@@ -143,7 +159,11 @@ __device__ __forceinline__ void pack_cost(const StepInput<NR, DT>& in, int nvali
             c0 = (2 * r < nvalid) ? c0 : 127u;
             c1 = (2 * r + 1 < nvalid) ? c1 : 127u;
         }
+#ifdef SGM_COST_IMAD
+        C[r] = c1 * 65536u + c0;                                           // FMA pipe instead of the ALU pipe's PRMT
+#else
         C[r] = __byte_perm(c0, c1, 0x5410);
+#endif
     }
 }
 
@@ -281,7 +301,11 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
             c0 = (dbase + 2 * r <= x) ? c0 : 127u;
             c1 = (dbase + 2 * r + 1 <= x) ? c1 : 127u;
         }
+#ifdef SGM_COST_IMAD
+        st.C[r] = c1 * 65536u + c0;
+#else
         st.C[r] = __byte_perm(c0, c1, 0x5410);
+#endif
     }
     int dg = (int)g - (int)st.g;
     dg = dg < 0 ? -dg : dg;
@@ -291,7 +315,7 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
 
 // n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
 // prepares the following step from lane i of the group.  WRAP: see dp_step.
-template <int NR, int LPP, bool FWD, bool BORDER, bool WRAP, typename DT>
+template <int NR, int LPP, bool FWD, bool BORDER, bool WRAP, typename DT, bool FULL_BLOCK = false>
 __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD, DT>& st, const uint32_t (&padm)[NR], int n,
                                                  int xnext, uint32_t gBlk, DT clBlk, DT crBlk, int sub, int dbase,
                                                  uint8_t*& out, long long outStride, bool stores)
@@ -320,7 +344,7 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
         for (int i = 0; i < n; i += DPL) {
 #pragma unroll
             for (int t = 0; t < DPL; ++t) {
-                if (i + t >= n) break;
+                if (!FULL_BLOCK && i + t >= n) break;
                 chain();
                 // inputs of the next step (independent of the chain above)
                 horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i + t, FWD ? xnext + i + t : xnext - i - t, sub, dbase, t);
@@ -422,6 +446,8 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
         // (two code variants only: the border one is also correct, just slower, for interior columns)
         const bool slow = border || prevBorder || P.wrapInterior != 0;
         if (slow) horizontal_block<NR, LPP, FWD, true, true, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        else if (n == LPP && LPP % DPL == 0)   // a whole block of interior steps: no end-of-row test inside the unrolled chunk
+                  horizontal_block<NR, LPP, FWD, false, false, DT, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         else      horizontal_block<NR, LPP, FWD, false, false, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         prevBorder = border;
         done += n;
@@ -631,14 +657,35 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
 // PAD = false: the disparity range fills every lane of every layout exactly (D == LPPH*2*NRH == LPPV*2*NRV ==
 // 64*NRI), so the masks that park unused disparity slots at 255 vanish (they cost ~50 of ~220 instructions per
 // visit when the compiler rematerialises them in the loop).
+#ifdef SGM_AGG_TRACE
+// Profiling build only (scripts/micro/agg_trace.py): start / end time, SM and direction of every warp job.
+constexpr int kAggTraceWarps = 65536;
+__device__ unsigned long long g_aggTrace[kAggTraceWarps * 3];
+struct AggTraceScope {
+    int widx, dir; unsigned long long t0;
+    __device__ AggTraceScope(int w, int d) : widx(w), dir(d) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0)); }
+    __device__ ~AggTraceScope() {
+        unsigned long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        if ((threadIdx.x & 31) == 0 && widx < kAggTraceWarps) {
+            g_aggTrace[3 * widx] = t0; g_aggTrace[3 * widx + 1] = t1; g_aggTrace[3 * widx + 2] = ((unsigned long long)dir << 32) | smid;
+        }
+    }
+};
+#endif
+
 template <int NRH, int LPPH, int NRV, int LPPV, int NRI, typename DT, bool PAD>
-__global__ void __launch_bounds__(kAggWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kAggWarpsPerBlock * 32, 16 / kAggWarpsPerBlock)
 sgm_aggregate_paths(const __grid_constant__ AggParams P)
 {
     const int widx = blockIdx.x * kAggWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (widx >= P.nIrregularWarps + P.nRegularWarps) return;
     const WarpWork job = P.work[widx];
+#ifdef SGM_AGG_TRACE
+    AggTraceScope trace(widx, widx < P.nIrregularWarps ? 8 + job.dir : job.dir);
+#endif
     if (widx < P.nIrregularWarps) aggregate_irregular<NRI, DT, PAD>(P, job, lane);
     else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT, PAD>(P, job, lane);
     else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD>(P, job, lane);

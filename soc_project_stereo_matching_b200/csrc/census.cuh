@@ -8,12 +8,12 @@
 // (3 rows, 4 columns) stays 0, stage skipped for W <= 9 or H <= 7 (parity pinned only by the oracle's
 // own generalisation, see oracle/sgm_oracle.h).
 //
-// Layout produced (DT = descriptor type, K = 16 / sizeof(DT) descriptors per 128-bit load):
+// Layout produced (DT = descriptor type, K = 32 / sizeof(DT) descriptors per 256-bit load):
 //   left  : DT [H*W]
 //   right : K copies, copy a shifted right by a elements inside a zero-padded array:
 //           right[a][padF + a + p] = census(p).  K2 needs, per lane, 2..16 consecutive right descriptors
-//           cR[q-k]; picking the copy with (padF + a + q - (n-1)) % K == 0 turns that window into
-//           aligned 64/128-bit loads for every pixel position q.
+//           cR[q-k]; picking the copy with (padF + a + q - (n-1)) % min(n, K) == 0 turns that window into
+//           aligned 64/128/256-bit loads for every pixel position q.
 // The image tile (+ halo) is staged in shared memory.
 //
 // PLANAR = true fuses the colour -> grey conversion of the board's frame format into the staging pass: the
@@ -35,7 +35,7 @@ struct CensusParams {
     void* pixL;              // {left descriptor, grey value} per pixel of the LEFT image: uint2 (32-bit descriptors) or
                              // uint4 {lo, hi, grey, 0} (64-bit descriptors)
     void* right4;            // DT [K][copyStride]
-    size_t copyStride;       // elements per copy (padF + N + padB, multiple of 4)
+    size_t copyStride;       // elements per copy (padF + N + padB, multiple of 8)
     int padF;
     int W, H;
 };
@@ -52,7 +52,7 @@ sgm_census(CensusParams P)
     // tile of 64 x 8 outputs, (64 + CW - 1) x (8 + CH - 1) inputs; every thread produces four horizontally adjacent outputs:
     // their windows span 4 + CW - 1 columns, fetched as 32-bit words (2 per row for 5x5, 3 for 9x7: 10 loads instead of the
     // 100 byte loads of four separate windows), the bytes picked with PRMT at compile-time positions
-    constexpr int RX = CW / 2, RY = CH / 2, K = 16 / (int)sizeof(DT), PX = kCensusPerThread;
+    constexpr int RX = CW / 2, RY = CH / 2, K = 32 / (int)sizeof(DT), PX = kCensusPerThread;
     constexpr int TW = kCensusTileW + CW - 1, TH = kCensusTileH + CH - 1, TP = (TW + 3 + 3) & ~3, NWORD = (PX + CW - 1 + 3) / 4;
     __shared__ __align__(16) uint8_t tile[TH][TP];
     const int which = blockIdx.z;
@@ -92,48 +92,84 @@ sgm_census(CensusParams P)
     const int ty = threadIdx.x / (kCensusTileW / PX);
     const int tx = (threadIdx.x % (kCensusTileW / PX)) * PX;
     const int y = y0 + ty;
-    if (y >= H) return;
-    uint32_t b[CH][PX + CW - 1];                              // b[r][c] = tile[ty + r][tx + c]: every byte is extracted once for all four windows
+    // Right image, 32-bit descriptors: the tile's descriptors are parked in shared memory and every shifted copy is then
+    // written as aligned 128-bit pieces (below); all threads of the block stay for that pass.
+    constexpr bool kStagedCopies = sizeof(DT) == 4;
+    __shared__ uint32_t parked[kStagedCopies ? kCensusTileH : 1][kStagedCopies ? kCensusTileW + 4 : 1];   // + 4: neighbouring rows start four banks apart
+    const bool viaShared = kStagedCopies && which == 1;
+    if (y >= H && !viaShared) return;
+    if (y < H) {
+        uint32_t b[CH][PX + CW - 1];                              // b[r][c] = tile[ty + r][tx + c]: every byte is extracted once for all four windows
 #pragma unroll
-    for (int r = 0; r < CH; ++r)
+        for (int r = 0; r < CH; ++r)
 #pragma unroll
-        for (int k = 0; k < NWORD; ++k) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[ty + r][tx + 4 * k]);
+            for (int k = 0; k < NWORD; ++k) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[ty + r][tx + 4 * k]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (4 * k + j < PX + CW - 1) b[r][4 * k + j] = __byte_perm(w, 0u, 0x4440u | (uint32_t)j);
+                for (int j = 0; j < 4; ++j)
+                    if (4 * k + j < PX + CW - 1) b[r][4 * k + j] = __byte_perm(w, 0u, 0x4440u | (uint32_t)j);
+            }
+        auto px = [&](int r, int c) -> uint32_t { return b[r][c]; };
+#pragma unroll
+        for (int o = 0; o < PX; ++o) {
+            const int x = x0 + tx + o;
+            if (x >= W) break;
+            DT bits = 0;
+            const uint32_t centre = px(RY, o + RX);
+            if (y >= RY && y < H - RY && x >= RX && x < W - RX && W > CW && H > CH) {
+                // "neighbour < centre" is the sign of (neighbour - centre); a funnel shift moves it into the descriptor: two
+                // instructions per comparison.  64-bit descriptors are built as two 32-bit words (the last 32 comparisons: low word).
+                uint32_t acc[2] = {0u, 0u};
+#pragma unroll
+                for (int r = 0; r < CH; ++r)
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) {
+                        constexpr int total = CW * CH;
+                        const int word = (sizeof(DT) == 8 && r * CW + c < total - 32) ? 0 : 1;
+                        acc[word] = __funnelshift_l(px(r, o + c) - centre, acc[word], 1);
+                    }
+                bits = (DT)acc[1];
+                if (sizeof(DT) == 8) bits |= (DT)((unsigned long long)acc[0] << 32);
+            }
+            const size_t p = (size_t)y * W + x;
+            if (which == 0) {
+                static_cast<DT*>(P.left)[p] = bits;
+                const uint32_t grey = centre;
+                if (sizeof(DT) == 4) static_cast<uint2*>(P.pixL)[p] = make_uint2((uint32_t)bits, grey);
+                else static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
+            } else if (kStagedCopies) {
+                parked[ty][tx + o] = (uint32_t)bits;
+            } else {
+#pragma unroll
+                for (int a = 0; a < K; ++a) static_cast<DT*>(P.right4)[a * P.copyStride + P.padF + a + p] = bits;
+            }
         }
-    auto px = [&](int r, int c) -> uint32_t { return b[r][c]; };
-#pragma unroll
-    for (int o = 0; o < PX; ++o) {
-        const int x = x0 + tx + o;
-        if (x >= W) break;
-        DT bits = 0;
-        const uint32_t centre = px(RY, o + RX);
-        if (y >= RY && y < H - RY && x >= RX && x < W - RX && W > CW && H > CH) {
-            // "neighbour < centre" is the sign of (neighbour - centre); a funnel shift moves it into the descriptor: two
-            // instructions per comparison.  64-bit descriptors are built as two 32-bit words (the last 32 comparisons: low word).
-            uint32_t acc[2] = {0u, 0u};
-#pragma unroll
-            for (int r = 0; r < CH; ++r)
-#pragma unroll
-                for (int c = 0; c < CW; ++c) {
-                    constexpr int total = CW * CH;
-                    const int word = (sizeof(DT) == 8 && r * CW + c < total - 32) ? 0 : 1;
-                    acc[word] = __funnelshift_l(px(r, o + c) - centre, acc[word], 1);
-                }
-            bits = (DT)acc[1];
-            if (sizeof(DT) == 8) bits |= (DT)((unsigned long long)acc[0] << 32);
-        }
-        const size_t p = (size_t)y * W + x;
-        if (which == 0) {
-            static_cast<DT*>(P.left)[p] = bits;
-            const uint32_t grey = centre;
-            if (sizeof(DT) == 4) static_cast<uint2*>(P.pixL)[p] = make_uint2((uint32_t)bits, grey);
-            else static_cast<uint4*>(P.pixL)[p] = make_uint4((uint32_t)bits, (uint32_t)((unsigned long long)bits >> 32), grey, 0u);
-        } else {
-#pragma unroll
-            for (int a = 0; a < K; ++a) static_cast<DT*>(P.right4)[a * P.copyStride + P.padF + a + p] = bits;
+    }
+    if (!viaShared) return;
+    // The K shifted copies of the tile's rows: copy a, tile row r = elements [e0, e0 + cols) of that copy with
+    // e0 = padF + a + (y0 + r) * W + x0.  A (copy, row) pair belongs to 16 consecutive threads: thread s writes the s-th
+    // aligned 128-bit piece, the thread behind the last piece the <= 3 elements before the first and after the last one.
+    // (One 4-byte store per copy and output - 32 per thread - made this kernel 19.5 us at C2 with eight copies.)
+    __syncthreads();
+    if constexpr (kStagedCopies) {
+        const int cols = min(kCensusTileW, W - x0);
+        const int slot = threadIdx.x & 15;
+        uint32_t* const copies = static_cast<uint32_t*>(P.right4);
+#pragma unroll 2
+        for (int pair = threadIdx.x >> 4; pair < K * kCensusTileH; pair += kCensusThreads / 16) {
+            const int a = pair / kCensusTileH, r = pair % kCensusTileH;
+            if (y0 + r >= H) continue;
+            const size_t e0 = (size_t)P.padF + a + (size_t)(y0 + r) * W + x0;
+            uint32_t* const dst = copies + a * P.copyStride + e0;
+            const int lead = min((int)((0 - e0) & 3), cols);
+            const int nfull = (cols - lead) >> 2;
+            if (slot < nfull) {
+                const uint32_t* q = &parked[r][lead + 4 * slot];
+                *reinterpret_cast<uint4*>(dst + lead + 4 * slot) = make_uint4(q[0], q[1], q[2], q[3]);
+            } else if (slot == nfull) {                                // nfull <= 15 whenever there is a partial piece
+                for (int i = 0; i < lead; ++i) dst[i] = parked[r][i];
+                for (int i = lead + 4 * nfull; i < cols; ++i) dst[i] = parked[r][i];
+            }
         }
     }
 }

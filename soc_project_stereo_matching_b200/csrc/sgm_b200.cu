@@ -62,7 +62,7 @@ struct Slot {
     cudaEvent_t evStart = nullptr, evStop = nullptr, evAgg0 = nullptr, evAgg1 = nullptr, evDone = nullptr, evCopied = nullptr;
     uint8_t* img[2] = {nullptr, nullptr};
     void* censusL = nullptr;          // descriptors: uint32 (5x5 census) or 64-bit (9x7 census)
-    void* censusR4 = nullptr;         // [16 / descBytes][copyStride] shifted copies (census.cuh)
+    void* censusR4 = nullptr;         // [32 / descBytes][copyStride] shifted copies (census.cuh)
     void* pixL = nullptr;             // {left descriptor, grey} per pixel: uint2 / uint4 for 32- / 64-bit descriptors (aggregate.cuh)
     uint8_t* planes = nullptr;
     uint16_t* side = nullptr;
@@ -362,11 +362,11 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->imgStride = (c->N + 16 + 255) & ~(size_t)255;
     c->NR = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
     c->descBytes = (c->censusW == 9 && c->censusH == 7) ? 8 : 4;
-    const int nCopies = 16 / c->descBytes;
+    const int nCopies = 32 / c->descBytes;            // shifted copies of the right census: any window starts 32-byte aligned in one of them
     c->Dp = (D + 15) & ~15;
     c->nDirs = (option->num_paths == 4) ? 4 : 8;      // the reference ignores num_paths (always 8)
-    c->padF = ((option->min_disparity + 64 * c->NR + 8) + 3) & ~3;
-    c->copyStride = ((size_t)c->padF + c->N + 16 + 3) & ~(size_t)3;
+    c->padF = ((option->min_disparity + 64 * c->NR + 8) + 7) & ~7;
+    c->copyStride = ((size_t)c->padF + c->N + 16 + 7) & ~(size_t)7;
     c->planeStride = c->N * (size_t)c->Dp;
     // K3 addresses the planes with 32-bit indices in 16-byte units (wta.cuh)
     if (7 * (c->planeStride >> 4) >= ((size_t)1 << 32))
@@ -442,7 +442,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     std::vector<WarpWork> work(irregular);
     work.insert(work.end(), regular.begin(), regular.end());
     c->nIrregularWarps = (int)irregular.size();
-    c->nRegularWarps = (int)regular.size();
+    c->nRegularWarps = (int)(work.size() - irregular.size());
     c->nEntries = nEntries;
     c->nIrregular = (int)irregular.size();
     CU(cudaMalloc(&c->work, work.size() * sizeof(WarpWork)));
@@ -493,6 +493,15 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     c->configured = true;
     return SGMB_OK;
 }
+
+#ifdef SGM_AGG_TRACE
+extern "C" int SGMB_DebugAggTrace(unsigned long long* dst, int nWarps)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(dst, g_aggTrace, (size_t)std::min(nWarps, kAggTraceWarps) * 3 * sizeof(unsigned long long)));
+    return SGMB_OK;
+}
+#endif
 
 extern "C" int SGMB_SetCensusWindow(SGMB_Context* c, int width, int height)
 {
@@ -1275,7 +1284,7 @@ extern "C" double SGMB_PlanBytesPerFrame(SGMB_Context* c)
 {
     if (!c || !c->configured) return 0.0;
     // planes written once by K2 and read once by K3 (Dp bytes per pixel and direction), census/images/disparity per pixel
-    return (double)c->N * (2.0 * c->nDirs * c->Dp + 2 + 4 + 4 * 4 + 4 * 4 + 4);
+    return (double)c->N * (2.0 * c->nDirs * c->Dp + 2 + 4 + 8 * 4 + 8 * 4 + 4);
 }
 
 extern "C" float SGMB_LastDeviceMs(SGMB_Context* c) { return c ? c->lastMs : -1.f; }
