@@ -18,11 +18,12 @@ __device__ __forceinline__ bool pp_valid(float d) { return d != __int_as_float(0
 // Connected components over the 8-neighbourhood; two valid neighbours are connected when |d_a - d_b| <= diff
 // (SemiGlobalMatching.c:620-624); components smaller than min_speckle_area become invalid (:633-638).
 //
-// Union-find on pixel indices (links always point to a smaller index, so the forest is acyclic), organised so
+// Union-find on pixel indices (init links every pixel to the first pixel of its run; unions link ROOTS only, the root with
+// the larger scrambled index below the other one, so the forest is acyclic and shallow), organised so
 // that a single huge component - the normal case for a good disparity map - costs almost nothing:
-//   init   every pixel is linked to the first pixel of its horizontal run inside its 32-pixel warp segment
-//          (one ballot), segments of one run are chained through their first pixel; so rows are merged without
-//          a single atomic;
+//   init   every pixel is linked to the first pixel of its horizontal run (one ballot per 32-pixel segment, the
+//          run that crosses a segment boundary carried along the row by the warp that owns the row); so rows are
+//          merged without a single atomic and every find starts one link away from a run's first pixel;
 //   merge  only the unions that are not implied by others are executed: the vertical link below a pixel is
 //          skipped when the same two rows are already linked one column to the left, a diagonal link when the
 //          corresponding horizontal + vertical links exist; finds split the path they walk;
@@ -36,16 +37,28 @@ __device__ __forceinline__ bool pp_edge(float a, float b, float diff)
 // Lock-free union-find in the standard form: only ROOTS are ever linked (compare-and-swap root -> smaller node), so a
 // link that a finished union relies on is never replaced by anything but a link to one of its ancestors.
 // Root of x with path splitting: every node on the walked path is re-pointed to its grandparent.  The stores are
-// plain: the node written is a non-root (forever, links only decrease) and the value is one of its ancestors, so
+// plain: the node written is a non-root (forever: roots are only ever linked, never unlinked) and the value is one of its ancestors, so
 // concurrent writers can only disagree about WHICH ancestor.  Loads bypass L1 (another SM may have linked the node).
+#ifdef SGM_SPECKLE_DEBUG
+__device__ unsigned long long g_ufStats[8];       // finds, hops, longest walk, unions asked, CAS failures
+#endif
 __device__ __forceinline__ int uf_find(int* lab, int x)
 {
     int p = __ldcg(lab + x);
+#ifdef SGM_SPECKLE_DEBUG
+    unsigned hops = 0;
+#endif
     while (p != x) {
         const int gp = __ldcg(lab + p);
         if (gp != p) lab[x] = gp;
         x = p; p = gp;
+#ifdef SGM_SPECKLE_DEBUG
+        ++hops;
+#endif
     }
+#ifdef SGM_SPECKLE_DEBUG
+    atomicAdd(&g_ufStats[0], 1ull); atomicAdd(&g_ufStats[1], (unsigned long long)hops); atomicMax(&g_ufStats[2], (unsigned long long)hops);
+#endif
     return x;
 }
 
@@ -58,42 +71,80 @@ __device__ __forceinline__ int uf_root(const int* lab, int x)
     return x;
 }
 
+__device__ __forceinline__ unsigned uf_key(int x) { return (unsigned)x * 0x9E3779B1u; }
+
 __device__ __forceinline__ void uf_union(int* lab, int a, int b)
 {
+#ifdef SGM_SPECKLE_DEBUG
+    atomicAdd(&g_ufStats[3], 1ull);
+#endif
     for (;;) {
         a = uf_find(lab, a);
         b = uf_find(lab, b);
         if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }       // the larger root is linked below the smaller one
+        // The root with the larger KEY is linked below the other one.  Any strict total order keeps the forest acyclic; with
+        // the pixel index as the key every row's run linked to the run above it and the big component of a good map became a
+        // chain hundreds of links deep that the first finds had to walk (longest walk measured at C2: 51 links with eight
+        // paths, 102 with four - and speckle_merge took about 0.45 us per link of that walk).  A scrambled index (an odd
+        // multiplier is a bijection on 32 bits) links in random order: expected depth O(log n).
+        if (uf_key(a) < uf_key(b)) { const int t = a; a = b; b = t; }
         const int old = atomicCAS(lab + a, a, b);
+#ifdef SGM_SPECKLE_DEBUG
+        if (old != a) atomicAdd(&g_ufStats[4], 1ull);
+#endif
         if (old == a) return;
         a = old;                                            // a had been linked meanwhile: continue from its parent
     }
 }
 
-// grid (ceil(W/32), ceil(H/8)), block (32, 8): one warp per 32-pixel row segment, eight rows per CTA (one-warp CTAs -
-// 14625 of them at C2 - were bound by the CTA launch rate: 14 us for a kernel that moves 4 MB).
-constexpr int kSpeckleRowsPerBlock = 8;
-__global__ void __launch_bounds__(32 * kSpeckleRowsPerBlock) speckle_init(const float* __restrict__ disp, int* __restrict__ lab,
-                                                                        int* __restrict__ size, int W, int H, float diff)
+// grid ceil(H / 4), block (32, 4): ONE WARP PER IMAGE ROW, walking its 32-pixel segments from left to right, so that every
+// pixel is linked DIRECTLY to the first pixel of its horizontal run however many segments the run spans (the first pixel
+// of the run that reaches the end of a segment is carried to the next one in a register).  Before, a segment was chained
+// to the previous one through its first pixel, and a find from the far end of a run of k segments walked 2k links - each an
+// L2 round trip; speckle_merge and speckle_count, which are nothing but finds, took 24 + 16 us at C2.  The loads of a
+// batch of eight segments are issued together (they do not depend on the carried value).
+constexpr int kSpeckleRowsPerBlock = 8;            // speckle_merge / speckle_count: rows per CTA
+constexpr int kSpeckleInitRowsPerBlock = 4;
+__global__ void __launch_bounds__(32 * kSpeckleInitRowsPerBlock) speckle_init(const float* __restrict__ disp, int* __restrict__ lab,
+                                                                            int* __restrict__ size, int W, int H, float diff)
 {
-    const int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y * kSpeckleRowsPerBlock + threadIdx.y;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x, y = blockIdx.x * kSpeckleInitRowsPerBlock + threadIdx.y;
     if (y >= H) return;                                              // whole warps leave together
-    const bool in = x < W;
-    const int p = y * W + x;
-    const float d = in ? disp[p] : __int_as_float(0x7f800000);
-    const float left = (in && x > 0) ? disp[p - 1] : __int_as_float(0x7f800000);
-    const bool valid = in && pp_valid(d);
-    const bool joined = valid && pp_edge(d, left, diff);             // connected to the pixel on its left
-    const unsigned starts = __ballot_sync(0xffffffffu, valid && !joined);
-    if (!in) return;
-    size[p] = 0;
-    if (!valid) { lab[p] = -1; return; }
-    const unsigned below = starts & (0xffffffffu >> (31 - lane));    // run starts at lanes <= mine
-    const int segBase = p - lane;
-    if (below)          lab[p] = segBase + (31 - __clz(below));      // first pixel of the run inside this segment
-    else if (lane == 0) lab[p] = p - 1;                              // the run began in an earlier segment: chain to its last pixel
-    else                lab[p] = segBase;                            // ... through this segment's first pixel
+    const float inf = __int_as_float(0x7f800000);
+    const int rowBase = y * W;
+    int carry = -1;                                                  // first pixel of the run that reaches the end of the previous segment
+    float prevLast = inf;                                            // disparity of the previous segment's last pixel
+    constexpr int B = 8;                                             // segments per batch: their loads are issued together
+    for (int xb = 0; xb < W; xb += 32 * B) {
+        float dv[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int x = xb + 32 * k + lane;
+            dv[k] = x < W ? __ldg(disp + rowBase + x) : inf;
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int x0 = xb + 32 * k;
+            if (x0 >= W) break;                                      // warp-uniform
+            const int x = x0 + lane, p = rowBase + x;
+            const bool in = x < W;
+            const float d = dv[k];
+            float left = __shfl_up_sync(FULL, d, 1);
+            if (lane == 0) left = prevLast;
+            const bool valid = in && pp_valid(d);
+            const bool joined = valid && pp_edge(d, left, diff);     // connected to the pixel on its left
+            const unsigned starts = __ballot_sync(FULL, valid && !joined);
+            int label = -1;
+            if (valid) {
+                const unsigned below = starts & (0xffffffffu >> (31 - lane));    // run starts at lanes <= mine
+                label = below ? rowBase + x0 + (31 - __clz(below)) : carry;      // no start up to here: the run came in from the left
+            }
+            if (in) { size[p] = 0; lab[p] = label; }
+            carry = __shfl_sync(FULL, label, 31);
+            prevLast = __shfl_sync(FULL, d, 31);
+        }
+    }
 }
 
 __global__ void speckle_merge(const float* __restrict__ disp, int* lab, int W, int H, float diff)
@@ -143,7 +194,7 @@ static int launch_speckle_labels(const float* in, int32_t* scratch /* [2N] */, i
     int* lab = scratch;
     int* size = scratch + n;
     dim3 b(32, kSpeckleRowsPerBlock), g((W + 31) / 32, (H + kSpeckleRowsPerBlock - 1) / kSpeckleRowsPerBlock);
-    speckle_init<<<g, b, 0, st>>>(in, lab, size, W, H, diff);
+    speckle_init<<<(H + kSpeckleInitRowsPerBlock - 1) / kSpeckleInitRowsPerBlock, dim3(32, kSpeckleInitRowsPerBlock), 0, st>>>(in, lab, size, W, H, diff);
     mark("speckle_init");
     speckle_merge<<<g, b, 0, st>>>(in, lab, W, H, diff);
     mark("speckle_merge");

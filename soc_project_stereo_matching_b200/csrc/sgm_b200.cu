@@ -494,6 +494,16 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     return SGMB_OK;
 }
 
+#ifdef SGM_SPECKLE_DEBUG
+extern "C" int SGMB_DebugUfStats(unsigned long long* dst, int reset)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(dst, g_ufStats, sizeof(g_ufStats)));
+    if (reset) { unsigned long long z[8] = {}; CU(cudaMemcpyToSymbol(g_ufStats, z, sizeof z)); }
+    return SGMB_OK;
+}
+#endif
+
 #ifdef SGM_AGG_TRACE
 extern "C" int SGMB_DebugAggTrace(unsigned long long* dst, int nWarps)
 {
