@@ -447,9 +447,9 @@ def main() -> int:
             "timing": {"replays": int(max(1, args.replays)), "statistic": "median over replays of one CUDA graph of K frames (max over ranks)",
                        "ms_per_step_p95": p95_ms / args.steps, "ms_per_step_min": min_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},
             "latency_ms": {"median": float(np.median(lat_ms)), "p95": float(np.percentile(lat_ms, 95)), "note": "single frame, host sync + L2 flush between frames"},
-            "roofline": {"bound": "issue", "bound_note": "dependent-instruction latency / issue rate of the integer DP (ALU pipe), not HBM: see frac_measured_traffic",
+            "roofline": {"bound": "issue", "bound_note": "instruction issue of the integer DP (four resident warps per scheduler at ~0.5 issued per cycle, ALU pipe ~2/3 busy), not HBM: see frac_measured_traffic",
                          "kernel": "sgm_aggregate_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "frac_note": "SURVEY 8d model: algorithmic bytes of the reference's formulation (S read-modify-written per direction)",
+                         "frac": achieved / peak, "frac_note": "SURVEY 8d model: algorithmic bytes of the reference's formulation (S read-modify-written per direction) / kernel time / peak; the kernel writes each path cost once as a byte and never re-reads S, so it moves 4x fewer bytes than the model and this number can exceed 1 - it says the kernel outruns an HBM-bound implementation of the reference's formulation, not that it is HBM-bound (frac_measured_traffic is the real HBM share)",
                          "traffic": traffic, "frac_measured_traffic": (traffic / (agg_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          "issue_frac": issue_frac, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": agg_alg_bytes, "kernel_ms": agg_avg_ms,
