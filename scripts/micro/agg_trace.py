@@ -56,3 +56,18 @@ if os.environ.get("DUMP_PLACEMENT"):
     for i, s_ in enumerate(cta_sm):
         order.setdefault(s_, []).append(i)
     print("per-SM CTA lists (first 12 SMs by id):", [(k, order[k]) for k in sorted(order)[:12]])
+if os.environ.get("DUMP_SLOWEST"):
+    byfin = sorted(rows)
+    def describe(r):
+        s_ = r[1]
+        cnt = collections.Counter(x[1] for x in per[s_])
+        last = max(per[s_])
+        return f"SM {s_:3d} finish {r[0]:6.1f} dirs {dict(sorted(cnt.items()))} last job dir {last[1]}"
+    print("slowest SMs:"); [print("  ", describe(r)) for r in byfin[-10:]]
+    hs = [r for r in byfin if r[3] == 4 and r[2] == 16]
+    print("fastest SMs with 4 horizontal + 12 column-like:"); [print("  ", describe(r)) for r in hs[:6]]
+    # when do the warps of each direction end on the slowest SM
+    s_ = byfin[-1][1]
+    print("jobs of the slowest SM:", sorted((round(e, 1), d_) for e, d_ in per[s_]))
+    s_ = hs[0][1]
+    print("jobs of the fastest 4+12 SM:", sorted((round(e, 1), d_) for e, d_ in per[s_]))

@@ -145,25 +145,32 @@ __device__ __forceinline__ void load_step(const AggParams& P, uint32_t pos, int 
     }
 }
 
+// Which two of the lane's 2*NR disparity indices share register r.  Natural pairing: (2r, 2r+1).  Paired ("strided") layout,
+// used by all regular paths when every layout of the launch owns whole 8-disparity units (NRH and NRV multiples of 4):
+// inside each unit of 8 indices register j of the unit holds (j, j + 4), so that the neighbours d-1 / d+1 of BOTH fields of
+// a register are simply the previous / next register - only the first and last register of a unit need a PRMT (2 per unit
+// instead of one per register: 4 instead of 9 per visit of the 8 x 16 layout, 2 instead of 5 per horizontal step).  The
+// plane bytes are stored as the registers lie (store_plane is the same code): unit byte order 0,4,1,5,2,6,3,7; K3 sums the
+// words as even / odd byte fields, which with this order ARE the natural pairs (wta.cuh), and SGMB_GetStage undoes it.
+__host__ __device__ constexpr bool agg_paired_layout(int nrh, int nrv) { return nrh % 4 == 0 && nrv % 4 == 0; }
+template <bool STR> __device__ __forceinline__ constexpr int pair_lo(int r) { return STR ? 8 * (r >> 2) + (r & 3) : 2 * r; }
+template <bool STR> __device__ __forceinline__ constexpr int pair_hi(int r) { return STR ? 8 * (r >> 2) + (r & 3) + 4 : 2 * r + 1; }
+
 // Matching cost of the lane's 2*NR disparities, packed two per register (SemiGlobalMatching.c:170-177).
 // BORDER: the pixel is so close to the left image edge that some right columns are negative -> cost 127
 // for disparity indices >= nvalid.
-template <int NR, bool BORDER, typename DT>
+template <int NR, bool BORDER, typename DT, bool STR>
 __device__ __forceinline__ void pack_cost(const StepInput<NR, DT>& in, int nvalid, uint32_t (&C)[NR])
 {
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        uint32_t c0 = desc_popc(in.cl ^ in.v[2 * NR - 1 - 2 * r]);
-        uint32_t c1 = desc_popc(in.cl ^ in.v[2 * NR - 2 - 2 * r]);
+        uint32_t c0 = desc_popc(in.cl ^ in.v[2 * NR - 1 - pair_lo<STR>(r)]);
+        uint32_t c1 = desc_popc(in.cl ^ in.v[2 * NR - 1 - pair_hi<STR>(r)]);
         if (BORDER) {
-            c0 = (2 * r < nvalid) ? c0 : 127u;
-            c1 = (2 * r + 1 < nvalid) ? c1 : 127u;
+            c0 = (pair_lo<STR>(r) < nvalid) ? c0 : 127u;
+            c1 = (pair_hi<STR>(r) < nvalid) ? c1 : 127u;
         }
-#ifdef SGM_COST_IMAD
-        C[r] = c1 * 65536u + c0;                                           // FMA pipe instead of the ALU pipe's PRMT
-#else
         C[r] = __byte_perm(c0, c1, 0x5410);
-#endif
     }
 }
 
@@ -171,21 +178,41 @@ __device__ __forceinline__ void pack_cost(const StepInput<NR, DT>& in, int nvali
 // at the ends of the disparity range).
 // WRAP = false: the caller guarantees C + (m - minPrev) <= 255 in every field (no cost of 127 in this visit and
 // max cost + largest P2 <= 255, AggParams::wrapInterior == 0), so the reference's uint8 truncation is the identity.
-template <int NR, bool WRAP = true>
+template <int NR, bool WRAP, bool STR>
 __device__ __forceinline__ void dp_step(uint32_t (&L)[NR], const uint32_t (&C)[NR], const uint32_t (&padm)[NR],
                                         uint32_t up, uint32_t dn, uint32_t p1x2, uint32_t p2x2, uint32_t negmin)
 {
-    uint32_t lm1 = __byte_perm(up, L[0], 0x5432);                          // Lp[d-1] of both fields of register 0
+    if constexpr (STR) {
+        static_assert(NR % 4 == 0, "paired layout: whole units of 8 disparities");
+        uint32_t o[NR];                                                    // the previous pixel's values (L is overwritten below)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const uint32_t above = (r == NR - 1) ? dn : L[r + 1];
-        const uint32_t lp1 = __byte_perm(L[r], above, 0x5432);             // Lp[d+1]; also Lp[d-1] of register r+1
-        uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[r]);                    // min(Lp[d-1]+P1, Lp[d])
-        t = __viaddmin_u16x2(lp1, p1x2, t);                                // min(Lp[d+1]+P1, .)
-        t = __viaddmin_u16x2(t, negmin, p2x2);                             // min(. - minPrev, P2')   in [0, 255]
-        const uint32_t sum = C[r] + t;                                     // fields <= 127 + 255: no carry between them
-        L[r] = (WRAP ? (sum & 0x00FF00FFu) : sum) | padm[r];               // (uint8)(C + m - minPrev)
-        lm1 = lp1;
+        for (int r = 0; r < NR; ++r) o[r] = L[r];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int u = r >> 2, j = r & 3;
+            // Lp[d-1] / Lp[d+1] of both fields: the neighbouring register, except at the ends of a unit, where the low field
+            // continues in the previous unit's last register (high field) / the high field in the next unit's first (low field)
+            const uint32_t lm1 = j > 0 ? o[r - 1] : __byte_perm(u == 0 ? up : o[4 * u - 1], o[4 * u + 3], 0x5432);
+            const uint32_t lp1 = j < 3 ? o[r + 1] : __byte_perm(o[4 * u], u == NR / 4 - 1 ? dn : o[4 * u + 4], 0x5432);
+            uint32_t t = __viaddmin_u16x2(lm1, p1x2, o[r]);
+            t = __viaddmin_u16x2(lp1, p1x2, t);
+            t = __viaddmin_u16x2(t, negmin, p2x2);
+            const uint32_t sum = C[r] + t;
+            L[r] = (WRAP ? (sum & 0x00FF00FFu) : sum) | padm[r];
+        }
+    } else {
+        uint32_t lm1 = __byte_perm(up, L[0], 0x5432);                      // Lp[d-1] of both fields of register 0
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t above = (r == NR - 1) ? dn : L[r + 1];
+            const uint32_t lp1 = __byte_perm(L[r], above, 0x5432);         // Lp[d+1]; also Lp[d-1] of register r+1
+            uint32_t t = __viaddmin_u16x2(lm1, p1x2, L[r]);                // min(Lp[d-1]+P1, Lp[d])
+            t = __viaddmin_u16x2(lp1, p1x2, t);                            // min(Lp[d+1]+P1, .)
+            t = __viaddmin_u16x2(t, negmin, p2x2);                         // min(. - minPrev, P2')   in [0, 255]
+            const uint32_t sum = C[r] + t;                                 // fields <= 127 + 255: no carry between them
+            L[r] = (WRAP ? (sum & 0x00FF00FFu) : sum) | padm[r];           // (uint8)(C + m - minPrev)
+            lm1 = lp1;
+        }
     }
 }
 
@@ -256,7 +283,7 @@ struct HorizontalState {
 // ROT >= 0: the window is kept as a ring in its registers -- logical element k lives in register (k -+ t) mod DPL at
 // chunk time t -- so that inside a fully unrolled chunk of DPL steps the slide costs no register moves; ROT is the
 // chunk time BEFORE this slide (after DPL slides logical == physical again).  ROT < 0: plain shifting registers.
-template <int NR, int LPP, bool FWD, bool BORDER, typename DT>
+template <int NR, int LPP, bool FWD, bool BORDER, typename DT, bool STR>
 __device__ __forceinline__ void horizontal_prepare(const AggParams& P, HorizontalState<NR, FWD, DT>& st, uint32_t gBlk, DT clBlk,
                                                    DT crBlk, int j, int x, int sub, int dbase, int ROT)
 {
@@ -295,17 +322,13 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        uint32_t c0 = desc_popc(cl ^ st.w[(base + 2 * r) % DPL]);
-        uint32_t c1 = desc_popc(cl ^ st.w[(base + 2 * r + 1) % DPL]);
+        uint32_t c0 = desc_popc(cl ^ st.w[(base + pair_lo<STR>(r)) % DPL]);
+        uint32_t c1 = desc_popc(cl ^ st.w[(base + pair_hi<STR>(r)) % DPL]);
         if (BORDER) {                                   // right column x - d < 0  ->  cost 127 (SemiGlobalMatching.c:170-172)
-            c0 = (dbase + 2 * r <= x) ? c0 : 127u;
-            c1 = (dbase + 2 * r + 1 <= x) ? c1 : 127u;
+            c0 = (dbase + pair_lo<STR>(r) <= x) ? c0 : 127u;
+            c1 = (dbase + pair_hi<STR>(r) <= x) ? c1 : 127u;
         }
-#ifdef SGM_COST_IMAD
-        st.C[r] = c1 * 65536u + c0;
-#else
         st.C[r] = __byte_perm(c0, c1, 0x5410);
-#endif
     }
     int dg = (int)g - (int)st.g;
     dg = dg < 0 ? -dg : dg;
@@ -315,7 +338,7 @@ __device__ __forceinline__ void horizontal_prepare(const AggParams& P, Horizonta
 
 // n steps whose inputs come from one block of registers: step i of the block consumes the prepared inputs and
 // prepares the following step from lane i of the group.  WRAP: see dp_step.
-template <int NR, int LPP, bool FWD, bool BORDER, bool WRAP, typename DT, bool FULL_BLOCK = false>
+template <int NR, int LPP, bool FWD, bool BORDER, bool WRAP, typename DT, bool STR, bool FULL_BLOCK = false>
 __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalState<NR, FWD, DT>& st, const uint32_t (&padm)[NR], int n,
                                                  int xnext, uint32_t gBlk, DT clBlk, DT crBlk, int sub, int dbase,
                                                  uint8_t*& out, long long outStride, bool stores)
@@ -331,7 +354,7 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
         uint32_t dn = __shfl_down_sync(FULL, st.L[0], 1, LPP);
         if (sub == 0) up = 0x00FF00FFu;
         if (sub == LPP - 1) dn = 0x00FF00FFu;
-        dp_step<NR, WRAP>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
+        dp_step<NR, WRAP, STR>(st.L, Ccur, padm, up, dn, P.p1x2, p2, __vneg2(st.minx2));
         st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
         if (stores) store_plane<NR>(out, st.L);
         out += outStride;
@@ -347,18 +370,18 @@ __device__ __forceinline__ void horizontal_block(const AggParams& P, HorizontalS
                 if (!FULL_BLOCK && i + t >= n) break;
                 chain();
                 // inputs of the next step (independent of the chain above)
-                horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i + t, FWD ? xnext + i + t : xnext - i - t, sub, dbase, t);
+                horizontal_prepare<NR, LPP, FWD, BORDER, DT, STR>(P, st, gBlk, clBlk, crBlk, i + t, FWD ? xnext + i + t : xnext - i - t, sub, dbase, t);
             }
         }
     } else {
         for (int i = 0; i < n; ++i) {
             chain();
-            horizontal_prepare<NR, LPP, FWD, BORDER, DT>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase, -1);
+            horizontal_prepare<NR, LPP, FWD, BORDER, DT, STR>(P, st, gBlk, clBlk, crBlk, i, FWD ? xnext + i : xnext - i, sub, dbase, -1);
         }
     }
 }
 
-template <int NR, int LPP, bool FWD, typename DT, bool PAD>
+template <int NR, int LPP, bool FWD, typename DT, bool PAD, bool STR>
 __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const WarpWork job, int lane)
 {
     constexpr int DPL = 2 * NR;
@@ -372,8 +395,8 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     uint32_t padm[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const int i0 = DPL * sub + 2 * r;
-        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
+        const int i0 = DPL * sub + pair_lo<STR>(r), i1 = DPL * sub + pair_hi<STR>(r);
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
     }
     const int dbase = P.dmin + DPL * sub;
     const int dlast = P.dmin + LPP * DPL - 1;
@@ -412,8 +435,8 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const uint32_t c0 = (dbase + 2 * r <= x0) ? desc_popc(cl ^ st.w[2 * r]) : 127u;
-            const uint32_t c1 = (dbase + 2 * r + 1 <= x0) ? desc_popc(cl ^ st.w[2 * r + 1]) : 127u;
+            const uint32_t c0 = (dbase + pair_lo<STR>(r) <= x0) ? desc_popc(cl ^ st.w[pair_lo<STR>(r)]) : 127u;
+            const uint32_t c1 = (dbase + pair_hi<STR>(r) <= x0) ? desc_popc(cl ^ st.w[pair_hi<STR>(r)]) : 127u;
             st.L[r] = (c1 * 65536u + c0) | padm[r];
         }
         st.minx2 = group_min_x2<LPP>(lane_min_x2<NR>(st.L));
@@ -422,7 +445,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
     }
     if (W == 1) return;
     // prepare step 1 from lane 0 of block 0; afterwards every block iteration consumes one step and prepares the next
-    horizontal_prepare<NR, LPP, FWD, true, DT>(P, st, gA, clA, crA, 0, column(1), sub, dbase, -1);
+    horizontal_prepare<NR, LPP, FWD, true, DT, STR>(P, st, gA, clA, crA, 0, column(1), sub, dbase, -1);
     // steps 1 .. W-1: step s is consumed in block (s-1)/LPP at i = (s-1)%LPP, where step s+1 is prepared from lane i+1
     // of the same block, or lane 0 of the next one.  To keep one loop body, rotate the block registers by one lane:
     // consuming position i prepares from lane i of registers that hold steps LPP*b+2 .. LPP*b+LPP+1.
@@ -445,10 +468,10 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
         // the first step a block consumes was prepared by the previous block: no truncation only if neither saw the border
         // (two code variants only: the border one is also correct, just slower, for interior columns)
         const bool slow = border || prevBorder || P.wrapInterior != 0;
-        if (slow) horizontal_block<NR, LPP, FWD, true, true, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        if (slow) horizontal_block<NR, LPP, FWD, true, true, DT, STR>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         else if (n == LPP && LPP % DPL == 0)   // a whole block of interior steps: no end-of-row test inside the unrolled chunk
-                  horizontal_block<NR, LPP, FWD, false, false, DT, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
-        else      horizontal_block<NR, LPP, FWD, false, false, DT>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+                  horizontal_block<NR, LPP, FWD, false, false, DT, STR, true>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
+        else      horizontal_block<NR, LPP, FWD, false, false, DT, STR>(P, st, padm, n, column(sPrepFirst), gS, clS, crS, sub, dbase, out, outStride, stores);
         prevBorder = border;
         done += n;
         gA = gB; clA = clB; crA = crB;
@@ -460,7 +483,7 @@ __device__ __forceinline__ void aggregate_horizontal(const AggParams& P, const W
 // with a constant stride (plus one column wrap for diagonals); 32/LPP paths of one direction share a warp and
 // every lane owns 2*NR disparities.  The loads of visit s+1 are issued before the dependent chain of visit s
 // (two input buffers, loop unrolled by two).
-template <int NR, int LPP, bool DIAG, typename DT, bool PAD>
+template <int NR, int LPP, bool DIAG, typename DT, bool PAD, bool STR>
 __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const WarpWork job, int lane)
 {
     static_assert(NR == 1 || NR == 2 || NR == 4 || NR == 8, "NR");
@@ -481,8 +504,8 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
     uint32_t padm[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const int i0 = DPL * sub + 2 * r;
-        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i0 + 1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
+        const int i0 = DPL * sub + pair_lo<STR>(r), i1 = DPL * sub + pair_hi<STR>(r);
+        padm[r] = PAD ? ((i0 >= P.D ? 0x000000FFu : 0u) | (i1 >= P.D ? 0x00FF0000u : 0u)) : 0u;
     }
     const int dbase = P.dmin + DPL * sub;                 // absolute disparity of this lane's first index
     const int dlast = P.dmin + DPL * LPP - 1;             // largest absolute disparity the group may hold
@@ -506,13 +529,13 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
     };
     auto cost = [&](const StepInput<NR, DT>& in, int tc) {
         const bool border = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
-        if (border) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
-        else pack_cost<NR, false, DT>(in, 0, C);
+        if (border) pack_cost<NR, true, DT, STR>(in, tc - dbase + 1, C);
+        else pack_cost<NR, false, DT, STR>(in, 0, C);
     };
     auto visit = [&](const StepInput<NR, DT>& in, uint32_t p, int tc) {
         const bool slow = DIAG ? (__any_sync(FULL, tc < dlast) != 0) : colBorder;
-        if (slow) pack_cost<NR, true, DT>(in, tc - dbase + 1, C);
-        else pack_cost<NR, false, DT>(in, 0, C);
+        if (slow) pack_cost<NR, true, DT, STR>(in, tc - dbase + 1, C);
+        else pack_cost<NR, false, DT, STR>(in, 0, C);
         int dg = (int)in.g - (int)gPrev;
         dg = dg < 0 ? -dg : dg;
         gPrev = in.g;
@@ -524,7 +547,7 @@ __device__ __forceinline__ void aggregate_column_like(const AggParams& P, const 
         if (sub == LPP - 1) dn = 0x00FF00FFu;     // Lp[DPL*LPP] = 255
         if (stores) store_plane<NR>(planeLane + (size_t)posPrev * P.Dp, L);   // emit the previous visit before overwriting L
         // (always with the uint8 truncation: a second copy of the step without it, selected per visit, measured 9 % slower)
-        dp_step<NR, true>(L, C, padm, up, dn, p1x2, p2x2, negmin);
+        dp_step<NR, true, STR>(L, C, padm, up, dn, p1x2, p2x2, negmin);
         minx2 = group_min_x2<LPP>(lane_min_x2<NR>(L));
         posPrev = p;
     };
@@ -620,7 +643,7 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
             inB[k] = (s + k < len) && inR[k];     // the reference's out-of-bounds visit is skipped (warp-uniform)
             eB[k] = eR[k];
             gB[k] = ring[k].g;
-            if (inB[k]) pack_cost<NR, true, DT>(ring[k], tcR[k] - dbase + 1, Cb[k]);
+            if (inB[k]) pack_cost<NR, true, DT, false>(ring[k], tcR[k] - dbase + 1, Cb[k]);
         }
 #pragma unroll
         for (int k = 0; k < kBlock; ++k)
@@ -639,7 +662,7 @@ __device__ __forceinline__ void aggregate_irregular(const AggParams& P, const Wa
                 uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
                 if (lane == 0) up = 0x00FF00FFu;
                 if (lane == 31) dn = 0x00FF00FFu;
-                dp_step<NR>(L, Cb[k], padm, up, dn, P.p1x2, P.p2x2[dg], __vneg2(minx2));
+                dp_step<NR, true, false>(L, Cb[k], padm, up, dn, P.p1x2, P.p2x2[dg], __vneg2(minx2));
             }
             minx2 = group_min_x2<32>(lane_min_x2<NR>(L));
             gPrev = gB[k];
@@ -686,11 +709,12 @@ sgm_aggregate_paths(const __grid_constant__ AggParams P)
 #ifdef SGM_AGG_TRACE
     AggTraceScope trace(widx, widx < P.nIrregularWarps ? 8 + job.dir : job.dir);
 #endif
+    constexpr bool STR = agg_paired_layout(NRH, NRV);     // register pairing of the regular paths = byte order of the planes
     if (widx < P.nIrregularWarps) aggregate_irregular<NRI, DT, PAD>(P, job, lane);
-    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT, PAD>(P, job, lane);
-    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD>(P, job, lane);
-    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT, PAD>(P, job, lane);
-    else                          aggregate_column_like<NRV, LPPV, true, DT, PAD>(P, job, lane);
+    else if (job.dir == 0)        aggregate_horizontal<NRH, LPPH, true, DT, PAD, STR>(P, job, lane);
+    else if (job.dir == 1)        aggregate_horizontal<NRH, LPPH, false, DT, PAD, STR>(P, job, lane);
+    else if (job.dir < 4)         aggregate_column_like<NRV, LPPV, false, DT, PAD, STR>(P, job, lane);
+    else                          aggregate_column_like<NRV, LPPV, true, DT, PAD, STR>(P, job, lane);
 }
 
 }  // namespace sgmb

@@ -611,6 +611,8 @@ static int enqueue_frame(SGMB_Context* c, Slot& s, const uint8_t* dL, const uint
         const bool pad = (D != 64 * c->NR) || (c->altLayout == 2);
 #define SGM_AGG_LAUNCH(NRH, LPPH, NRV, LPPV, NRI, DT)                                                          \
     do {                                                                                                       \
+        if (agg_paired_layout(NRH, NRV) != (c->wtaCPP >= 8))                                                   \
+            return fail(SGMB_E_STATE, "aggregation layout and plane byte order of the WTA kernel disagree");  \
         if (pad) sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, true><<<blocks, threads, 0, s.stream>>>(p);  \
         else     sgm_aggregate_paths<NRH, LPPH, NRV, LPPV, NRI, DT, false><<<blocks, threads, 0, s.stream>>>(p); \
     } while (0)
@@ -1239,6 +1241,16 @@ extern "C" int SGMB_GetStage(SGMB_Context* c, int stage, void* dst, size_t bytes
                 need = N * c->D;
                 if (bytes != need) return fail(SGMB_E_STATE, "SGMB_GetStage: stage %d needs %zu bytes, got %zu", stage, need, bytes);
                 const uint8_t* plane = s.planes + (size_t)(stage - SGMB_STAGE_PATH_PLANE_0) * c->planeStride;
+                if (c->wtaCPP >= 8) {
+                    // paired plane layout (aggregate.cuh): inside every unit of 8 disparities the bytes lie as 0,4,1,5,2,6,3,7
+                    std::vector<uint8_t> tmp(N * (size_t)c->Dp);
+                    CU(cudaMemcpy(tmp.data(), plane, tmp.size(), cudaMemcpyDeviceToHost));
+                    uint8_t* out = static_cast<uint8_t*>(dst);
+                    for (size_t px = 0; px < N; ++px)
+                        for (int d = 0; d < c->D; ++d)
+                            out[px * c->D + d] = tmp[px * c->Dp + (d & ~7) + 2 * (d & 3) + ((d >> 2) & 1)];
+                    return SGMB_OK;
+                }
                 CU(cudaMemcpy2D(dst, c->D, plane, c->Dp, c->D, N, cudaMemcpyDeviceToHost));
                 return SGMB_OK;
             }

@@ -141,6 +141,9 @@ struct WtaShape {
     static constexpr int kThreads = CPP == 16 ? 512 : 256;
     static constexpr int kTW = kThreads / CPP;          // columns per tile
     static constexpr int kRW = 8 * CPP + 4;             // ring row stride in 32-bit words (a multiple of 4: rows are 16-byte aligned)
+    // byte order of the planes: disparity ranges above 64 (CPP >= 8) run K2 with the paired register layout (aggregate.cuh,
+    // agg_paired_layout; checked against the launch table in enqueue_frame)
+    static constexpr bool kPairedPlanes = CPP >= 8;
     // ring rows: a multiple of the tile width, at least 2 * TW + D
     __host__ __device__ static constexpr int ring_rows(int D) { return 2 * kTW + ((D + kTW - 1) / kTW) * kTW; }
     __host__ __device__ static constexpr size_t ring_bytes(int D) { return (size_t)ring_rows(D) * kRW * 4; }
@@ -245,8 +248,15 @@ __device__ __forceinline__ void wta_segment(const WtaParams& P, uint32_t* ring, 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t ev = all[i] - (od[i] << 8);       // both even fields <= 8 * 255: exact mod 2^32
-                    out[2 * i] = __byte_perm(ev, od[i], 0x5410);
-                    out[2 * i + 1] = __byte_perm(ev, od[i], 0x7632);
+                    if constexpr (WtaShape<CPP>::kPairedPlanes) {
+                        // K2's paired register layout stores each unit of 8 disparities as bytes 0,4,1,5 | 2,6,3,7: the even
+                        // byte fields of word i ARE the pair (4(i/2)... ) in natural order and the odd ones the pair four further
+                        out[4 * (i >> 1) + (i & 1)] = ev;            // word 0: (d0,d1)  1: (d2,d3)  2: (d8,d9)  3: (d10,d11)
+                        out[4 * (i >> 1) + (i & 1) + 2] = od[i];     //         (d4,d5)     (d6,d7)     (d12,d13)   (d14,d15)
+                    } else {
+                        out[2 * i] = __byte_perm(ev, od[i], 0x5410);
+                        out[2 * i + 1] = __byte_perm(ev, od[i], 0x7632);
+                    }
                 }
                 if (eNow >= 0) {
                     const uint4* sp = reinterpret_cast<const uint4*>(P.side + (size_t)eNow * Dp + 16 * v);

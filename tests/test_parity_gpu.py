@@ -102,10 +102,11 @@ def test_against_oracle(ctx, oracle, w, h, tex, kw):
     compare_stages(f"{w}x{h}x{d}", got, want)
 
 
-def test_path_planes_match_oracle_on_regular_pixels(ctx, oracle):
+@pytest.mark.parametrize("w,h,d", [(80, 36, 32), (176, 20, 96), (200, 16, 128)])
+def test_path_planes_match_oracle_on_regular_pixels(ctx, oracle, w, h, d):
     """Per-direction tap: plane r equals the oracle's contribution of direction r wherever direction r's
-    regular paths are the only visitors; the planes plus the side buffer sum to S (checked via `aggr`)."""
-    w, h, d = 80, 36, 32
+    regular paths are the only visitors; the planes plus the side buffer sum to S (checked via `aggr`).
+    Disparity ranges above 64 store the planes in the paired byte order (aggregate.cuh) that the tap undoes."""
     opts = options(max_disparity=d)
     left, right, _ = make_pair(w, h, d, seed=7, texture="scene")
     want = oracle.match(left, right, opts, per_direction=True)
