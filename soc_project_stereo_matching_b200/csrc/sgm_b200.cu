@@ -390,7 +390,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
 
     // ---- path classification + work list (host walk of the 4*W diagonal paths; same walker as the kernel).
     //      32/lppH rows per warp for the horizontal directions, 32/lppV paths of one direction per warp otherwise.
-    //      Horizontal jobs first (measured: any other order is 6-8 % slower); all CTAs are co-resident at C2.
+    //      Horizontal jobs first (measured: any other position is 6-8 % slower); all CTAs are co-resident at C2.
     //      64-bit descriptors double the registers of the prefetched census windows, so that mode keeps 8
     //      disparities per lane up to D = 128 (must match the template arguments in enqueue_frame).
     c->lppV = (D <= 128 && !(c->descBytes == 8 && D > 64)) ? 8 : 16;
@@ -421,7 +421,13 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
     };
     auto all_paths = [&](int n) { std::vector<int> v(n); for (int i = 0; i < n; ++i) v[i] = i; return v; };
     // longest paths first: the horizontal directions have only H paths of W steps each
-    if (W >= H) { push_paths(0, all_paths(H), perWarpH); push_paths(1, all_paths(H), perWarpH); push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); }
+    // Landscape frames: the vertical directions go LAST.  All blocks of a KITTI-sized frame are resident at once, but the warp
+    // schedulers serve the warps of earlier blocks first (per-warp timeline, scripts/micro/agg_trace.py: the four blocks of an SM
+    // finish ~25 us apart in launch order although they start together), so the block that started last runs the end of its
+    // job alone, at a lone warp's issue rate; the vertical jobs are the cheapest per visit (no column wrap, border test once
+    // per warp) and make the shortest tail: 264.8 -> 262.7 us at C2.
+    const bool verticalLast = W >= H && !getenv("SGM_B200_DEBUG_VFIRST");
+    if (W >= H) { push_paths(0, all_paths(H), perWarpH); push_paths(1, all_paths(H), perWarpH); if (!verticalLast) { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); } }
     else        { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); push_paths(0, all_paths(H), perWarpH); push_paths(1, all_paths(H), perWarpH); }
     for (int d = 4; d < c->nDirs; ++d) {
         const Dir dir = direction(d);
@@ -438,6 +444,7 @@ extern "C" int SGMB_Configure(SGMB_Context* c, uint16_t width, uint16_t height, 
         }
         push_paths(d, reg, perWarpV);
     }
+    if (verticalLast) { push_paths(2, all_paths(W), perWarpV); push_paths(3, all_paths(W), perWarpV); }
     if (getenv("SGM_B200_DEBUG_NOIRR")) irregular.clear();      // profiling aid only (results are wrong when set)
     std::vector<WarpWork> work(irregular);
     work.insert(work.end(), regular.begin(), regular.end());
