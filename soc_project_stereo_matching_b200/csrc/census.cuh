@@ -147,28 +147,34 @@ sgm_census(CensusParams P)
     }
     if (!viaShared) return;
     // The K shifted copies of the tile's rows: copy a, tile row r = elements [e0, e0 + cols) of that copy with
-    // e0 = padF + a + (y0 + r) * W + x0.  A (copy, row) pair belongs to 16 consecutive threads: thread s writes the s-th
-    // aligned 128-bit piece, the thread behind the last piece the <= 3 elements before the first and after the last one.
+    // e0 = padF + a + (y0 + r) * W + x0.  A tile row belongs to 16 consecutive threads for all copies: thread s writes the s-th
+    // aligned 128-bit piece of each copy; the <= 3 elements before the first and after the last piece go to six of them.
     // (One 4-byte store per copy and output - 32 per thread - made this kernel 19.5 us at C2 with eight copies.)
     __syncthreads();
     if constexpr (kStagedCopies) {
         const int cols = min(kCensusTileW, W - x0);
         const int slot = threadIdx.x & 15;
         uint32_t* const copies = static_cast<uint32_t*>(P.right4);
-#pragma unroll 2
-        for (int pair = threadIdx.x >> 4; pair < K * kCensusTileH; pair += kCensusThreads / 16) {
-            const int a = pair / kCensusTileH, r = pair % kCensusTileH;
-            if (y0 + r >= H) continue;
-            const size_t e0 = (size_t)P.padF + a + (size_t)(y0 + r) * W + x0;
-            uint32_t* const dst = copies + a * P.copyStride + e0;
-            const int lead = min((int)((0 - e0) & 3), cols);
-            const int nfull = (cols - lead) >> 2;
-            if (slot < nfull) {
-                const uint32_t* q = &parked[r][lead + 4 * slot];
-                *reinterpret_cast<uint4*>(dst + lead + 4 * slot) = make_uint4(q[0], q[1], q[2], q[3]);
-            } else if (slot == nfull) {                                // nfull <= 15 whenever there is a partial piece
-                for (int i = 0; i < lead; ++i) dst[i] = parked[r][i];
-                for (int i = lead + 4 * nfull; i < cols; ++i) dst[i] = parked[r][i];
+        // thread -> (tile row r, slot) for every copy a in turn: eight (row, copy) pairs per thread, no loop over elements
+        const int r = threadIdx.x >> 4;                                // kCensusThreads / 16 == kCensusTileH rows
+        static_assert(kCensusThreads / 16 == kCensusTileH, "one group of 16 threads per tile row");
+        if (y0 + r < H) {
+            const size_t rowStart = (size_t)P.padF + (size_t)(y0 + r) * W + x0;
+            const uint32_t* const src = &parked[r][0];
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                const size_t e0 = rowStart + a;
+                uint32_t* const dst = copies + a * P.copyStride + e0;
+                const int lead = min((int)((0 - e0) & 3), cols);      // elements before the first aligned piece
+                const int nfull = (cols - lead) >> 2;                  // aligned 128-bit pieces (<= 16)
+                if (slot < nfull) {
+                    const uint32_t* q = src + lead + 4 * slot;
+                    *reinterpret_cast<uint4*>(dst + lead + 4 * slot) = make_uint4(q[0], q[1], q[2], q[3]);
+                }
+                // the <= 3 elements in front and the <= 3 behind the pieces: one thread each (slots 0-2 and 3-5)
+                if (slot < lead) dst[slot] = src[slot];
+                const int t = lead + 4 * nfull + slot - 3;
+                if (slot >= 3 && slot < 6 && t < cols) dst[t] = src[t];
             }
         }
     }
