@@ -252,7 +252,7 @@ __global__ void speckle_apply(const float* __restrict__ in, float* __restrict__ 
 //       allow ~5 per SM, ~740 per device; H = 65535 has 2048 groups).  The poll loop is bounded: a CTA that has
 //       waited ~2 s traps instead of hanging the device.
 constexpr int kMedianLaunches = 2;
-constexpr int kMedianTileW = 64;      // K5a: columns per block
+constexpr int kMedianTileW = 64;      // K5a: columns per block (32 for frames whose grid would not fill the device, see launch_median3_inplace)
 // One bulk copy per 32 steps: the per-block bookkeeping (mbarrier wait, warp syncs, proxy fence, re-arming the copy) costs
 // several hundred cycles of a lone warp, so the block is as long as the exchange batch allows (measured at C2: 4 steps per
 // block 281 us, 8: 216 us, 16: 197 us, 32: 176 us).
@@ -277,11 +277,12 @@ __device__ __forceinline__ void cswap(float& a, float& b)
 }
 
 // grid (ceil(W / 64), ceil(H / 32)), block 256.  `filtered` (optional tap) receives the speckle-filtered map.
+template <int TW>
 __global__ void __launch_bounds__(256)
 median_prepare(const float* __restrict__ in, const int* __restrict__ lab, const int* __restrict__ size, int minArea,
                float* __restrict__ filtered, float* __restrict__ prep, int W, int H)
 {
-    constexpr int TW = kMedianTileW, TS = TW + 3;        // row stride 67 = 3 (mod 32): lane l reads column s - 2l -> bank (l + s) % 32
+    constexpr int TS = TW + 3;                           // row stride 67 / 35 = 3 (mod 32): lane l reads column s - 2l -> bank (l + s) % 32
     __shared__ float tile[33][TS];                        // rows 32g .. 32g+32, columns j0-1 .. j0+TW
     const int g = blockIdx.y, j0 = blockIdx.x * TW, i0 = 32 * g;
     for (int k = threadIdx.x; k < 33 * (TW + 2); k += 256) {
@@ -598,8 +599,12 @@ static int launch_median3_inplace(const float* in, const int* lab, const int* si
 {
     *epoch = (*epoch % 65535u) + 1u;
     const int groups = (H + 31) / 32;
-    dim3 gp((W + kMedianTileW - 1) / kMedianTileW, groups);
-    median_prepare<<<gp, 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
+    // a block covers 32 rows x TW columns; with 64 columns a KITTI-sized frame has only 240 blocks for 148 SMs and the kernel
+    // is one round of dependent loads deep: 32 columns there (14.2 -> 12.3 us at C2); large frames keep 64 (C3: 46 vs 55 us)
+    if (((W + kMedianTileW - 1) / kMedianTileW) * groups < 4 * 148)
+        median_prepare<32><<<dim3((W + 31) / 32, groups), 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
+    else
+        median_prepare<kMedianTileW><<<dim3((W + kMedianTileW - 1) / kMedianTileW, groups), 256, 0, st>>>(in, lab, size, minArea, filteredTap, prep, W, H);
     mark("median_prepare");
     int* ticket = reinterpret_cast<int*>(xchg + (size_t)groups * W);
     median_wavefront<<<groups, 64, kMedianTileBytes, st>>>(prep, out, xchg, ticket, W, H, *epoch);
