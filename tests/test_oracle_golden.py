@@ -82,6 +82,33 @@ def test_oracle_matches_compiled_reference(oracle, w, h, tex, kw):
             assert_same(k, got[k], v)
 
 
+def _random_ref_cases(n=32, seed=20261019):
+    """Seeded draws over landscape shapes and every option the reference reads (SGM.h:24-40), incl. D up to 256."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        w = int(rng.integers(8, 97))
+        h = int(rng.integers(6, min(w, 48) + 1))
+        d = int(rng.choice([int(rng.integers(1, 33)), int(rng.integers(33, 129)), int(rng.integers(129, 257))]))
+        kw = dict(max_disparity=d, num_paths=int(rng.choice([4, 8])), p1=int(rng.integers(0, 40)),
+                  p2_init=int(rng.integers(0, 400)), check_unique=bool(rng.integers(0, 2)),
+                  uniqueness_ratio=float(rng.choice([0.8, 0.95, 0.99])), check_lr=bool(rng.integers(0, 2)),
+                  lrcheck_thres=float(rng.choice([0.5, 1.0, 2.0])), remove_speckles=bool(rng.integers(0, 2)),
+                  min_speckle_area=int(rng.integers(1, 80)))
+        out.append((w, h, str(rng.choice(["scene", "noise"])), kw))
+    return out
+
+
+@pytest.mark.parametrize("w,h,tex,kw", _random_ref_cases())
+def test_oracle_matches_compiled_reference_on_random_draws(oracle, w, h, tex, kw):
+    """Second pinning sweep: the restatement against the reference's own code on seeded random shapes and options
+    (every stage and every direction's path costs, bit for bit).  Runs where /root/reference is present."""
+    from build_ref import reference_available
+    if not reference_available():
+        pytest.skip("reference sources not available here (the sweep compiles the reference per shape)")
+    test_oracle_matches_compiled_reference(oracle, w, h, tex, kw)
+
+
 def test_oracle_rejects_what_the_reference_rejects(oracle):
     left = np.zeros((8, 8), np.uint8)
     with pytest.raises(ValueError):
