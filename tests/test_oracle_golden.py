@@ -90,7 +90,8 @@ def _random_ref_cases(n=32, seed=20261019):
         w = int(rng.integers(8, 97))
         h = int(rng.integers(6, min(w, 48) + 1))
         d = int(rng.choice([int(rng.integers(1, 33)), int(rng.integers(33, 129)), int(rng.integers(129, 257))]))
-        kw = dict(max_disparity=d, num_paths=int(rng.choice([4, 8])), p1=int(rng.integers(0, 40)),
+        mind = int(rng.integers(0, 7)) if i % 2 else 0
+        kw = dict(min_disparity=mind, max_disparity=mind + d, num_paths=int(rng.choice([4, 8])), p1=int(rng.integers(0, 40)),
                   p2_init=int(rng.integers(0, 400)), check_unique=bool(rng.integers(0, 2)),
                   uniqueness_ratio=float(rng.choice([0.8, 0.95, 0.99])), check_lr=bool(rng.integers(0, 2)),
                   lrcheck_thres=float(rng.choice([0.5, 1.0, 2.0])), remove_speckles=bool(rng.integers(0, 2)),
