@@ -39,6 +39,25 @@ def test_numpy_model_equals_c_oracle(oracle, w, h, tex, win, kw):
     assert np.array_equal(total, got["aggr"])
 
 
+def _random_cases(n=20, seed=97):
+    """Seeded draws: both census windows, landscape / square / portrait, D up to 96, penalties up to beyond uint8."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        w, h = int(rng.integers(10, 57)), int(rng.integers(8, 41))
+        d = int(rng.integers(1, 97))
+        mind = int(rng.integers(0, 6)) if i % 3 == 0 else 0
+        out.append((w, h, str(rng.choice(["scene", "noise"])), (9, 7) if i % 2 else (5, 5),
+                    dict(min_disparity=mind, max_disparity=mind + d, num_paths=int(rng.choice([4, 8])),
+                         p1=int(rng.choice([0, 5, 10, 40, 300])), p2_init=int(rng.choice([0, 90, 150, 400, 3000])))))
+    return out
+
+
+@pytest.mark.parametrize("w,h,tex,win,kw", _random_cases())
+def test_numpy_model_equals_c_oracle_on_random_draws(oracle, w, h, tex, win, kw):
+    test_numpy_model_equals_c_oracle(oracle, w, h, tex, win, kw)
+
+
 def test_numpy_walker_equals_the_library_and_the_oracle(oracle):
     import soc_project_stereo_matching_b200 as sgm
     for w, h in [(20, 12), (16, 16), (9, 8), (8, 9), (12, 20)]:
